@@ -1,0 +1,176 @@
+/*
+ * mcs.h - C ABI of libmcs_b200.so, the sm_100a implementation of the
+ * multicamera_stitching frame-compositing hot path.
+ *
+ * The reference (kiwicampus/multicamera_stitching) has no FFI layer: its seam
+ * is the Python class API of PostScripts/Stitcher/StitcherClass.py.  Each
+ * entry point below names the reference call(s) it replaces; INTEGRATION.md
+ * shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; image / descriptor / point buffers are
+ *     caller-owned DEVICE memory (raw CUDA device pointers), unless a
+ *     parameter is documented as "host";
+ *   - every function returns MCS_OK (0) or a negative MCS_ERR_* code, never
+ *     throws or aborts; mcs_last_error() gives the message for the calling
+ *     thread;
+ *   - work is enqueued on `cuda_stream` (a cudaStream_t, NULL = default
+ *     stream) and is asynchronous with respect to the host;
+ *   - the library allocates nothing the caller must free except mcs_plan.
+ */
+#ifndef MCS_B200_H
+#define MCS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCS_OK               0
+#define MCS_ERR_INVALID     -1   /* bad argument                              */
+#define MCS_ERR_CUDA        -2   /* a CUDA runtime / driver call failed       */
+#define MCS_ERR_UNSUPPORTED -3   /* valid request outside the built envelope  */
+#define MCS_ERR_NOMEM       -4
+
+#define MCS_MAX_LAYERS      16   /* cameras per panorama                      */
+
+/* layer kinds */
+#define MCS_LAYER_COPY       0   /* verbatim paste  (camera 0 / image B)      */
+#define MCS_LAYER_WARP       1   /* cv2.warpPerspective(INTER_LINEAR) resample */
+
+typedef struct mcs_plan mcs_plan;
+
+/* ABI version of this header (bumped on any signature change). */
+int mcs_abi_version(void);
+
+/* Message of the last error raised on the calling thread ("" if none). */
+const char* mcs_last_error(void);
+
+/*
+ * mcs_plan_create - flatten a calibrated stitcher chain into one compositing
+ * plan on the current CUDA device.
+ *
+ * Replaces the per-frame state walk of Stitcher.stitch (StitcherClass.py:
+ * 131-136) over StitcherBase.{cachedAH, Bpts, ABSize, AimgSize, BimgSize,
+ * x_limits, y_limits} (:193-209).  Layers are ordered innermost first: the
+ * value of output pixel p is taken from the FIRST layer whose rectangle
+ * contains p (that is the nested "paste imageB over the warped canvas" rule of
+ * StitcherClass.py:239-241 applied N-1 times); pixels in no rectangle are 0.
+ *
+ *   n_layers   1..MCS_MAX_LAYERS
+ *   channels   1, 3 or 4 (bytes per pixel of every source and of the output)
+ *   layer_kind [n]    MCS_LAYER_COPY | MCS_LAYER_WARP
+ *   src_hw     [n*2]  source frame (height, width) of each layer
+ *   fwd_h      [n*9]  row-major float64 FORWARD homography of each WARP layer,
+ *                     exactly the `M` the reference hands to
+ *                     cv2.warpPerspective (cachedAH); it is inverted here with
+ *                     the same closed form as cv::invert.  Ignored for COPY.
+ *   origin_xy  [n*2]  position, in output coordinates, of the origin of the
+ *                     layer's own canvas frame (for WARP: the frame cachedAH
+ *                     maps into; for COPY: where source pixel (0,0) lands)
+ *   rect_xyxy  [n*4]  half-open rectangle [x0,x1) x [y0,y1), in output
+ *                     coordinates, the layer (and everything it was pasted
+ *                     with) occupies
+ *   out_w,out_h       output panorama size (ABSize of the last stage, after
+ *                     the optional super-mode crop)
+ */
+int mcs_plan_create(mcs_plan** out, int n_layers, int channels,
+                    const int32_t* layer_kind, const int32_t* src_hw,
+                    const double* fwd_h, const int32_t* origin_xy,
+                    const int32_t* rect_xyxy, int out_w, int out_h);
+
+int mcs_plan_destroy(mcs_plan* plan);
+
+/*
+ * mcs_plan_owned_pixels - per-layer count of output pixels whose value is
+ * taken from that layer and has at least one bilinear tap inside the source
+ * (for COPY layers: every pixel of the visible rectangle).  Host array
+ * owned[n_layers].  This is the `owned_k` of SURVEY.md section 8(d):
+ *   algorithmic bytes / panorama = out_w*out_h*C + C * sum_k owned_k.
+ * Synchronous (runs a counting kernel on `cuda_stream` and waits).
+ */
+int mcs_plan_owned_pixels(const mcs_plan* plan, int64_t* owned_host, void* cuda_stream);
+
+/*
+ * mcs_stitch_u8 - composite n_frames panoramas.
+ *
+ * Replaces, per frame, the whole Stitcher.stitch chain (StitcherClass.py:
+ * 114-136): N-1 x { cv2.warpPerspective(imageA, cachedAH, ABSize) (:239),
+ * dst[By:By+hB, Bx:Bx+wB] = imageB (:240-241), super-mode crop (:248-251) }.
+ *
+ *   src              host array [n_layers] of device pointers, frame 0 of
+ *                    each layer's source (H x W x C uint8, rows
+ *                    src_pitch_bytes[k] apart)
+ *   src_pitch_bytes  host array [n_layers]
+ *   src_frame_stride host array [n_layers], bytes between consecutive frames
+ *                    of layer k (ignored when n_frames == 1)
+ *   dst              device pointer, frame 0 of the output
+ *                    (out_h x out_w x C uint8, rows dst_pitch_bytes apart)
+ * Every byte of the out_h x out_w*C window of each output frame is written
+ * exactly once; padding bytes between rows are left untouched.
+ */
+int mcs_stitch_u8(const mcs_plan* plan, const uint8_t* const* src,
+                  const int64_t* src_pitch_bytes, const int64_t* src_frame_stride,
+                  int n_frames, uint8_t* dst, int64_t dst_pitch_bytes,
+                  int64_t dst_frame_stride, void* cuda_stream);
+
+/* Which kernel variant the last mcs_stitch_u8 on this plan launched
+ * (diagnostics for tests / bench): 0 = none yet, 1 = gather, 2 = tiled. */
+int mcs_plan_last_variant(const mcs_plan* plan);
+
+/* Number of kernels this library has launched in the calling process. */
+int64_t mcs_launch_count(void);
+
+/*
+ * mcs_match_hamming_top2 - brute-force 2-nearest-neighbour Hamming matching
+ * plus Lowe's ratio test, for `batch` independent image pairs.
+ *
+ * Replaces matcher.knnMatch(featuresA, featuresB, 2) and the ratio loop of
+ * StitcherBase.matchKeypoints (StitcherClass.py:423-433) for binary (ORB)
+ * descriptors.
+ *
+ *   q, t        device, [batch][nq_max|nt_max][desc_bytes] uint8 descriptors
+ *               (query = featuresA, train = featuresB); desc_bytes % 4 == 0
+ *   nq, nt      device int32[batch] actual counts per pair, or NULL (= max)
+ *   ratio       keep[i] = dist0 < dist1 * ratio (evaluated in float64 like the
+ *               reference's Python expression), needs both neighbours
+ *   idx2,dist2  device int32 [batch][nq_max][2]: train indices / distances of
+ *               the best and second best match, ties broken toward the lower
+ *               train index (cv2 BFMatcher order); -1 where absent
+ *   keep        device uint8 [batch][nq_max]
+ */
+int mcs_match_hamming_top2(const uint8_t* q, const int32_t* nq, int nq_max,
+                           const uint8_t* t, const int32_t* nt, int nt_max,
+                           int desc_bytes, double ratio,
+                           int32_t* idx2, int32_t* dist2, uint8_t* keep,
+                           int batch, void* cuda_stream);
+
+/*
+ * mcs_ransac_homography - score `k` 4-point homography hypotheses per pair,
+ * one warp per hypothesis.
+ *
+ * Replaces the hypothesis loop inside cv2.findHomography(ptsA, ptsB, RANSAC,
+ * reprojThresh) (StitcherClass.py:443-444).
+ *
+ *   ptsA, ptsB   device float32 [batch][n_max][2] matched points (A -> B)
+ *   n            device int32[batch] point counts, or NULL (= n_max)
+ *   samples      device int32 [batch][k][4] point indices of each minimal
+ *                sample (host-seeded)
+ *   reproj_thresh  inlier iff squared reprojection error <= thresh^2
+ *   inlier_counts  device int32 [batch][k]  (-1 for a degenerate sample)
+ *   H_k            device float64 [batch][k][9] hypothesis homographies
+ *   best_idx       device int32 [batch]: argmax of inlier_counts (lowest
+ *                  index on ties), -1 if every sample was degenerate
+ *   best_mask      device uint8 [batch][n_max] inlier mask of the winner
+ */
+int mcs_ransac_homography(const float* ptsA, const float* ptsB, const int32_t* n,
+                          int n_max, const int32_t* samples, int k,
+                          float reproj_thresh, int32_t* inlier_counts,
+                          double* H_k, int32_t* best_idx, uint8_t* best_mask,
+                          int batch, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCS_B200_H */

@@ -1,0 +1,443 @@
+"""B200-native ``Stitcher`` / ``StitcherBase``.
+
+Drop-in for the classes of the reference's
+``PostScripts/Stitcher/StitcherClass.py`` (same class, method, argument and
+attribute names, same return conventions and graceful-degradation behaviour),
+re-implemented for Python 3 with the per-frame work moved onto the GPU:
+
+* ``Stitcher.stitch`` (reference :114-136) no longer runs N-1 sequential
+  ``cv2.warpPerspective`` + paste stages; the calibrated chain is flattened
+  once into a compositing plan and every panorama is ONE launch of the fused
+  warp+paste kernel behind ``mcs_stitch_u8`` (include/mcs.h).
+* ``StitcherBase.matchKeypoints`` (reference :405-448) runs the brute-force
+  Hamming 2-NN + ratio test and the RANSAC hypothesis scoring on the GPU
+  (``mcs_match_hamming_top2`` / ``mcs_ransac_homography``).
+
+Frames may be ``numpy`` arrays (result: a new ``numpy`` array, like the
+reference) or uint8 CUDA tensors (result: a CUDA tensor, nothing leaves the
+device).  There is no CPU fallback: without the CUDA library these methods
+raise.
+"""
+import os
+import pickle
+
+import cv2
+import numpy as np
+
+from .extended_rospylogs import Debugger, DEBUG_LEVEL_0
+from .Utils import get_projection_point_dst
+from .plan import PlanUnsupported
+
+# ---------------------------------------------------------------------------
+
+
+def get_opencv_major_version(lib=None):
+    """Major version number of OpenCV (reference :41-47)."""
+    if lib is None:
+        lib = cv2
+    return int(lib.__version__.split(".")[0])
+
+
+def is_cv3(or_better=False):
+    """Reference :30-39."""
+    major = get_opencv_major_version()
+    return major >= 3 if or_better else major == 3
+
+
+def _is_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda")
+
+
+def _shape_of(img):
+    return tuple(int(v) for v in img.shape)
+
+
+# ---------------------------------------------------------------------------
+class Stitcher(Debugger):
+    """N-camera panorama: a chain of N-1 pairwise stitchers (reference :50-177)."""
+
+    def __init__(self, images_dic, super_mode=False):
+        # labels sorted like np.sort(images_dic.keys()) (reference :61)
+        self.img_labels = np.sort(list(images_dic.keys()))
+        self.stitcher_labels = []
+        for idx in range(len(self.img_labels) - 1):
+            left = self.img_labels[idx] if idx == 0 else self.stitcher_labels[-1]
+            self.stitcher_labels.append("({}&{})".format(left, self.img_labels[idx + 1]))
+        self.stitchers = [StitcherBase(sid=label, super_mode=super_mode)
+                          for label in self.stitcher_labels]
+
+    # -- engine plumbing (never pickled) -------------------------------------
+    def _engine_(self):
+        eng = self.__dict__.get("_engine")
+        if eng is None:
+            from .engine import CompositeEngine
+            eng = CompositeEngine()
+            self.__dict__["_engine"] = eng
+        return eng
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_engine", None)
+        return state
+
+    # -- calibration ---------------------------------------------------------
+    def calibrate_stitcher(self, images_dic, save=True, save_path=""):
+        """Calibrate every pairwise stitcher on ``images_dic`` and optionally
+        save the configuration (reference :77-112).  Stage ``k`` calibrates the
+        next camera against the canvas stitched so far."""
+        img_result = None
+        for idx in range(len(self.img_labels) - 1):
+            if idx == 0:
+                images = (images_dic[self.img_labels[0]], images_dic[self.img_labels[1]])
+            else:
+                images = (img_result, images_dic[self.img_labels[idx + 1]])
+            self.stitchers[idx].calibrate(images=images, ratio=0.75, reprojThresh=3.0,
+                                          xoffset=0, yoffset=0)
+            img_result = self.stitchers[idx].stitch(images=images)
+        self._report()
+        if save:
+            self.save_stitcher(save_path)
+
+    def calibrate_from_homographies(self, img_shapes, homographies, xoffset=0, yoffset=0):
+        """Calibrate the chain from known homographies instead of matched
+        features (extension used for fixed rigs and synthetic benchmarks).
+        ``homographies[k]`` maps camera ``k+1`` into the canvas of stage
+        ``k-1`` (camera 0's frame for ``k == 0``), i.e. it is what
+        ``matchKeypoints`` would have returned at stage ``k``."""
+        shapeB = tuple(img_shapes[0])
+        for idx, H in enumerate(homographies):
+            st = self.stitchers[idx]
+            st.set_homography(H, shapeA=tuple(img_shapes[idx + 1]), shapeB=shapeB,
+                              xoffset=xoffset, yoffset=yoffset)
+            shapeB = st.result_shape()
+        self.__dict__.pop("_engine", None)
+
+    def _report(self):
+        for st in self.stitchers:
+            self.debugger(DEBUG_LEVEL_0, "[STITCHER]: {}".format(st),
+                          log_type="err" if st.status is None else "info")
+
+    # -- per-frame path --------------------------------------------------------
+    def stitch(self, images_dic, draw_descriptors=False):
+        """Stitched panorama of ``images_dic`` (reference :114-136)."""
+        if len(images_dic) > len(self.img_labels):
+            self.debugger(DEBUG_LEVEL_0, "[STITCHER] Images dictionary is bigger than list", log_type="warn")
+        elif len(images_dic) < len(self.img_labels):
+            self.debugger(DEBUG_LEVEL_0, "[STITCHER] Images dictionary is inferior to labels list",
+                          log_type="err")
+            return images_dic[self.img_labels[-1]]
+        if len(self.img_labels) < 2:
+            return images_dic[self.img_labels[-1]]
+        frames = [images_dic[label] for label in self.img_labels]
+        out = _composite(self._engine_(), self.stitchers, frames, batched=False, debugger=self)
+        if draw_descriptors and not _is_tensor(out):
+            # the reference draws every stage's overlay into the canvas it produced (:244-245);
+            # only the last stage's overlay is in final-panorama coordinates
+            out = self.stitchers[-1].draw_descriptors(img_src=out)
+        return out
+
+    def stitch_batch(self, frames_dic, out=None):
+        """Composite ``F`` frame-sets in one launch.  ``frames_dic[label]`` is a
+        uint8 CUDA tensor ``[F, H, W, C]``; returns (or fills ``out``) a CUDA
+        tensor ``[F, H_out, W_out, C]``.  Extension of the reference API."""
+        frames = [frames_dic[label] for label in self.img_labels]
+        return _composite(self._engine_(), self.stitchers, frames, batched=True, out=out, debugger=self)
+
+    def plan(self, img_shapes, device=None):
+        """Compiled plan (``engine.CompiledPlan``) for frames of these shapes."""
+        return self._engine_().plan_for(self.stitchers, [tuple(s) for s in img_shapes], device)
+
+    # -- persistence -----------------------------------------------------------
+    def save_stitcher(self, save_path):
+        """Pickle the whole object (reference :138-152)."""
+        try:
+            with open(save_path, "wb") as output:
+                for st in self.stitchers:
+                    st.params_to_list()
+                try:
+                    pickle.dump(self, output, pickle.HIGHEST_PROTOCOL)
+                finally:
+                    for st in self.stitchers:
+                        st.params_to_array()
+            self.debugger(DEBUG_LEVEL_0, "[STITCHER]: Stitcher configuration saved")
+        except IOError as e:
+            self.debugger(DEBUG_LEVEL_0,
+                          "[STITCHER]: Problem saving Stitcher configuration: {}".format(e), log_type="err")
+
+    def load_stitcher(self, load_path):
+        """Load a pickled configuration and RETURN the loaded object - callers
+        rebind, exactly like the reference (:154-177)."""
+        loaded = self
+        try:
+            if os.path.isfile(load_path):
+                with open(load_path, "rb") as f:
+                    loaded = _load_pickle(f)
+                for st in loaded.stitchers:
+                    st.params_to_array()
+                loaded.debugger(DEBUG_LEVEL_0, "[STITCHER]: Stitcher configuration loaded from file")
+            else:
+                self.debugger(DEBUG_LEVEL_0, "[STITCHER]: No Stitcher configuration file", log_type="warn")
+        except IOError as e:
+            self.debugger(DEBUG_LEVEL_0,
+                          "[STITCHER]: Problem saving Stitcher configuration: {}".format(e), log_type="err")
+        loaded._report()
+        return loaded
+
+
+# ---------------------------------------------------------------------------
+class StitcherBase(Debugger):
+    """One pair (imageB = running canvas, imageA = next camera), reference :180-529."""
+
+    def __init__(self, sid=None, super_mode=False):
+        self.sid = sid
+        self.super_mode = super_mode
+        self.descriptor = "ORB"   # BASELINE.json config 4; "SIFT" = the reference's detector
+        self.nfeatures = 2000
+        self.reset()
+
+    def reset(self):
+        """Back to the uncalibrated state (reference :507-525)."""
+        self.cachedBH = None
+        self.cachedBINVH = None
+        self.Bpts = None
+        self.cachedAH = None
+        self.cachedAINVH = None
+        self.Apts = None
+        self.matches = None
+        self.status = None
+        self.ABSize = None
+        self.x_limits = None
+        self.y_limits = None
+        self.AimgSize = None
+        self.BimgSize = None
+        self.__dict__.pop("_engine", None)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_engine", None)
+        return state
+
+    def __str__(self):
+        return "Stitcher:{}| Matches:{}| StitcherSize:{}".format(
+            self.sid, len(self.matches) if self.matches is not None else 0, self.ABSize)
+
+    def _engine_(self):
+        eng = self.__dict__.get("_engine")
+        if eng is None:
+            from .engine import CompositeEngine
+            eng = CompositeEngine()
+            self.__dict__["_engine"] = eng
+        return eng
+
+    # -- per-frame path --------------------------------------------------------
+    def stitch(self, images, draw_descriptors=False):
+        """Stitch ``(imageB, imageA)`` (reference :211-256)."""
+        imageB, imageA = images
+        if self.cachedAH is None:
+            return imageB
+        out = _composite(self._engine_(), [self], [imageB, imageA], batched=False, debugger=self)
+        if draw_descriptors and not _is_tensor(out):
+            out = self.draw_descriptors(img_src=out)
+        return out
+
+    def result_shape(self):
+        """``ndarray.shape`` of what :meth:`stitch` returns once calibrated."""
+        w, h = self.ABSize
+        if self.super_mode:
+            y0, y1, _ = slice(self.y_limits[0], self.y_limits[1]).indices(h)
+            x0, x1, _ = slice(self.x_limits[0], self.x_limits[1]).indices(w)
+            h, w = max(0, y1 - y0), max(0, x1 - x0)
+        return (h, w) + tuple(self.AimgSize[2:])
+
+    # -- calibration -----------------------------------------------------------
+    def calibrate(self, images, ratio=0.75, reprojThresh=4.0, xoffset=10, yoffset=10):
+        """Find the homography taking imageA into imageB's frame from matched
+        features and derive the canvas geometry (reference :258-354)."""
+        self.reset()
+        imageB, imageA = images
+        if _is_tensor(imageA):
+            imageA = imageA.cpu().numpy()
+        if _is_tensor(imageB):
+            imageB = imageB.cpu().numpy()
+        self.BimgSize = imageB.shape
+        self.AimgSize = imageA.shape
+        kpsA, featuresA = self.detectAndDescribe(imageA)
+        kpsB, featuresB = self.detectAndDescribe(imageB)
+        if kpsA is None or kpsB is None:
+            return
+        H, self.matches, self.status = self.matchKeypoints(
+            kpsA=kpsA, kpsB=kpsB, featuresA=featuresA, featuresB=featuresB,
+            ratio=ratio, reprojThresh=reprojThresh)
+        if H is not None:
+            self._geometry(H, xoffset, yoffset)
+        else:
+            self.reset()
+
+    def set_homography(self, H, shapeA, shapeB, xoffset=10, yoffset=10):
+        """Calibrate from a known homography (imageA -> imageB frame)."""
+        matches, status = self.matches, self.status
+        self.reset()
+        self.matches, self.status = matches, status
+        self.BimgSize = tuple(shapeB)
+        self.AimgSize = tuple(shapeA)
+        self._geometry(H, xoffset, yoffset)
+
+    def _geometry(self, H, xoffset, yoffset):
+        """Canvas geometry, reference :273-274 and :293-351.  Quirks kept on
+        purpose: corner projections are ``int()``-truncated (Utils.py:33-35),
+        the size uses ``abs(max(...))``, ROI limits split at half the canvas."""
+        xoffset = abs(xoffset)
+        yoffset = abs(yoffset)
+        hA, wA = self.AimgSize[0], self.AimgSize[1]
+        hB, wB = self.BimgSize[0], self.BimgSize[1]
+        H = np.array(H, dtype=np.float64)
+        cornersA = [(0, 0), (wA, 0), (wA, hA), (0, hA)]
+        Apts = [get_projection_point_dst(pt_src=(p[0], p[1], 1), M=H) for p in cornersA]
+        Bpts = [(0, 0), (wB, 0), (wB, hB), (0, hB)]
+        both = np.concatenate((Apts, Bpts), axis=0)
+        x_min = min(p[0] for p in both)
+        y_min = min(p[1] for p in both)
+
+        self.cachedBH = np.float32([[1, 0, x_min + xoffset], [0, 1, y_min + yoffset], [0, 0, 1]])
+        self.cachedBINVH = np.linalg.inv(self.cachedBH)
+        H[0][2] += -x_min + xoffset
+        H[1][2] += -y_min + yoffset
+        self.cachedAH = H
+        self.cachedAINVH = np.linalg.inv(H)
+
+        xoff = -x_min + xoffset
+        yoff = -y_min + yoffset
+        self.Bpts = [(xoff, yoff), (xoff + wB, yoff), (xoff + wB, hB + yoff), (xoff, hB + yoff)]
+        self.Apts = [get_projection_point_dst(pt_src=(p[0], p[1], 1), M=H) for p in cornersA]
+        pts = np.concatenate((self.Apts, self.Bpts), axis=0)
+        xs = [p[0] for p in pts]
+        ys = [p[1] for p in pts]
+        self.ABSize = (int(abs(max(xs)) + xoffset), int(abs(max(ys)) + yoffset))
+        self.x_limits = [max([v for v in xs if v < self.ABSize[0] * 0.5]),
+                         min([v for v in xs if v > self.ABSize[0] * 0.5])]
+        self.y_limits = [max([v for v in ys if v < self.ABSize[1] * 0.5]),
+                         min([v for v in ys if v > self.ABSize[1] * 0.5])]
+
+    def detectAndDescribe(self, image):
+        """Key-points (float32 N x 2) and descriptors of ``image`` (reference
+        :356-403).  Detection stays on the host;
+        ORB-2000 is BASELINE.json's recalibration workload, ``descriptor =
+        "SIFT"`` selects the reference's detector."""
+        if self.descriptor == "SIFT":
+            if not hasattr(cv2, "SIFT_create"):
+                self.debugger(DEBUG_LEVEL_0, "OpenCV has no SIFT implementation", log_type="err")
+                return None, None
+            det = cv2.SIFT_create()
+        else:
+            det = cv2.ORB_create(nfeatures=self.nfeatures)
+        kps, features = det.detectAndCompute(image, None)
+        if features is None:
+            return None, None
+        kps = np.float32([kp.pt for kp in kps]).reshape(-1, 2)
+        return kps, features
+
+    def matchKeypoints(self, kpsA, kpsB, featuresA, featuresB, ratio=0.75, reprojThresh=4.0):
+        """2-NN matching + Lowe ratio test + RANSAC homography (reference
+        :405-448).  Returns ``(H, matches, status)`` with ``matches`` a list of
+        ``(trainIdx, queryIdx)``."""
+        from . import recalib
+        return recalib.match_keypoints(kpsA, kpsB, featuresA, featuresB, ratio, reprojThresh)
+
+    def draw_descriptors(self, img_src):
+        """Debug overlay of corners / ROI limits (reference :450-483)."""
+        white = (255, 255, 255)
+        if self.Bpts is not None:
+            cv2.drawContours(img_src, np.array([self.Bpts], dtype=np.int32), -1, white, 1)
+            for pt in self.Bpts:
+                p = (int(pt[0]), int(pt[1]))
+                cv2.circle(img_src, p, 2, (0, 0, 255), -1)
+                cv2.circle(img_src, p, 5, (0, 255, 255), 1)
+        if self.Apts is not None:
+            cv2.drawContours(img_src, np.array([self.Apts], dtype=np.int32), -1, white, 1)
+            for pt in self.Apts:
+                p = (int(pt[0]), int(pt[1]))
+                cv2.circle(img_src, p, 2, (0, 0, 255), -1)
+                cv2.circle(img_src, p, 3, (255, 255, 0), 1)
+        if self.x_limits is not None:
+            for v in self.x_limits:
+                cv2.line(img_src, (int(v), 0), (int(v), img_src.shape[0]), (0, 255, 0), 1)
+        if self.y_limits is not None:
+            for v in self.y_limits:
+                cv2.line(img_src, (0, int(v)), (img_src.shape[1], int(v)), (255, 255, 0), 1)
+        cv2.putText(img_src, "{}".format(self.sid), (20, 20), cv2.FONT_HERSHEY_SIMPLEX, 0.60,
+                    (0, 255, 255), 1, cv2.LINE_AA)
+        return img_src
+
+    # -- persistence helpers -----------------------------------------------------
+    _MATRICES = ("cachedBH", "cachedBINVH", "cachedAH", "cachedAINVH")
+
+    def params_to_list(self):
+        """Matrices -> lists of rows before pickling (reference :485-494)."""
+        for name in self._MATRICES:
+            if getattr(self, name) is not None:
+                setattr(self, name, list(getattr(self, name)))
+
+    def params_to_array(self):
+        """Lists of rows -> arrays after loading (reference :496-505)."""
+        for name in self._MATRICES:
+            if getattr(self, name) is not None:
+                setattr(self, name, np.asarray(getattr(self, name)))
+
+
+# ---------------------------------------------------------------------------
+def _composite(engine, stages, frames, batched, out=None, debugger=None):
+    """Run the fused kernel for this chain on these frames."""
+    import torch  # local: keeps `import StitcherClass` cheap for calibration-only users
+
+    on_device = _is_tensor(frames[0]) and frames[0].is_cuda
+    shapes = [_shape_of(f)[1:] if batched else _shape_of(f) for f in frames]
+    device = frames[0].device if on_device else None
+    try:
+        plan = engine.plan_for(stages, shapes, device)
+    except PlanUnsupported as e:
+        if debugger is not None:
+            debugger.debugger(DEBUG_LEVEL_0, "[STITCHER] {}".format(e), log_type="err")
+        raise
+    if plan is None:
+        return frames[0]  # nothing calibrated: imageB passes through (reference :255-256)
+    if on_device:
+        n = int(frames[0].shape[0]) if batched else None
+        return plan.run(frames, out=out, n_frames=n)
+    if batched:
+        raise TypeError("stitch_batch expects uint8 CUDA tensors")
+    with torch.cuda.device(plan.device):
+        dev = [None] * len(frames)
+        for l in plan.flat.layers:
+            dev[l.cam] = engine.upload(l.cam, frames[l.cam], plan.device)
+        res = plan.run(dev)
+        host = torch.empty(res.shape, dtype=torch.uint8)
+        host.copy_(res)  # synchronous D2H into a fresh array, like cv2 allocating its result
+    return host.numpy()
+
+
+class _CompatUnpickler(pickle.Unpickler):
+    """Resolve classes pickled by the reference (module ``StitcherClass``,
+    possibly under Python 2) to this module's classes."""
+
+    def find_class(self, module, name):
+        if name == "Stitcher":
+            return Stitcher
+        if name == "StitcherBase":
+            return StitcherBase
+        if module.startswith("extended_rospylogs") and name == "Debugger":
+            return Debugger
+        return super().find_class(module, name)
+
+
+def _load_pickle(f):
+    data = f.read()
+    try:
+        return _CompatUnpickler(_BytesReader(data)).load()
+    except (UnicodeDecodeError, TypeError):
+        # Python-2 pickles carry byte strings
+        return _CompatUnpickler(_BytesReader(data), encoding="latin1").load()
+
+
+def _BytesReader(data):
+    import io
+    return io.BytesIO(data)

@@ -1,0 +1,154 @@
+"""ctypes binding of ``libmcs_b200.so`` (declared in ``include/mcs.h``).
+
+There is deliberately no fallback: if the library is missing or fails to load,
+or if a call returns an error code, an exception is raised.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libmcs_b200.so")
+
+MCS_OK = 0
+MCS_MAX_LAYERS = 16
+MCS_LAYER_COPY = 0
+MCS_LAYER_WARP = 1
+ABI_VERSION = 1
+
+# every symbol include/mcs.h declares
+EXPORTS = (
+    "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_destroy",
+    "mcs_plan_owned_pixels", "mcs_stitch_u8", "mcs_plan_last_variant", "mcs_launch_count",
+    "mcs_match_hamming_top2", "mcs_ransac_homography",
+)
+
+
+class McsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_c_i32p = ctypes.POINTER(ctypes.c_int32)
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+_c_f64p = ctypes.POINTER(ctypes.c_double)
+_vp = ctypes.c_void_p
+
+
+def load(build_if_missing=False):
+    """Load (once) and return the ctypes handle of the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            from . import build as _build
+            _build.build()
+        else:
+            raise McsError(
+                "%s not found: build it with `python -m multicamera_stitching_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mcs_abi_version.restype = ctypes.c_int
+    lib.mcs_abi_version.argtypes = []
+    if lib.mcs_abi_version() != ABI_VERSION:
+        raise McsError("libmcs_b200.so ABI %d != binding ABI %d - rebuild"
+                       % (lib.mcs_abi_version(), ABI_VERSION))
+    lib.mcs_last_error.restype = ctypes.c_char_p
+    lib.mcs_last_error.argtypes = []
+    lib.mcs_plan_create.restype = ctypes.c_int
+    lib.mcs_plan_create.argtypes = [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _c_i32p, _c_i32p,
+                                    _c_f64p, _c_i32p, _c_i32p, ctypes.c_int, ctypes.c_int]
+    lib.mcs_plan_destroy.restype = ctypes.c_int
+    lib.mcs_plan_destroy.argtypes = [_vp]
+    lib.mcs_plan_owned_pixels.restype = ctypes.c_int
+    lib.mcs_plan_owned_pixels.argtypes = [_vp, _c_i64p, _vp]
+    lib.mcs_stitch_u8.restype = ctypes.c_int
+    lib.mcs_stitch_u8.argtypes = [_vp, ctypes.POINTER(_vp), _c_i64p, _c_i64p, ctypes.c_int, _vp,
+                                  ctypes.c_int64, ctypes.c_int64, _vp]
+    lib.mcs_plan_last_variant.restype = ctypes.c_int
+    lib.mcs_plan_last_variant.argtypes = [_vp]
+    lib.mcs_launch_count.restype = ctypes.c_int64
+    lib.mcs_launch_count.argtypes = []
+    lib.mcs_match_hamming_top2.restype = ctypes.c_int
+    lib.mcs_match_hamming_top2.argtypes = [_vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_double, _vp, _vp, _vp, ctypes.c_int, _vp]
+    lib.mcs_ransac_homography.restype = ctypes.c_int
+    lib.mcs_ransac_homography.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_float,
+                                          _vp, _vp, _vp, _vp, ctypes.c_int, _vp]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != MCS_OK:
+        msg = load().mcs_last_error().decode(errors="replace")
+        raise McsError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def launch_count():
+    return int(load().mcs_launch_count())
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_c_i32p)
+
+
+class Plan(object):
+    """Owning wrapper of an ``mcs_plan*``."""
+
+    def __init__(self, layer_kind, src_hw, fwd_h, origin_xy, rect_xyxy, out_w, out_h, channels):
+        lib = load()
+        n = len(layer_kind)
+        kind, kind_p = _i32(layer_kind)
+        hw, hw_p = _i32(np.reshape(src_hw, (n, 2)))
+        org, org_p = _i32(np.reshape(origin_xy, (n, 2)))
+        rect, rect_p = _i32(np.reshape(rect_xyxy, (n, 4)))
+        h = np.ascontiguousarray(np.reshape(fwd_h, (n, 9)), dtype=np.float64)
+        handle = _vp()
+        check(lib.mcs_plan_create(ctypes.byref(handle), n, int(channels), kind_p, hw_p,
+                                  h.ctypes.data_as(_c_f64p), org_p, rect_p, int(out_w), int(out_h)),
+              "mcs_plan_create")
+        self._h = handle
+        self.n_layers = n
+        self.channels = int(channels)
+        self.out_w = int(out_w)
+        self.out_h = int(out_h)
+        self.src_hw = hw.copy()
+        self._owned = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and _lib is not None:
+            _lib.mcs_plan_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def stitch(self, src_ptrs, src_pitch, src_frame_stride, n_frames, dst_ptr, dst_pitch,
+               dst_frame_stride, stream=0):
+        n = self.n_layers
+        ptrs = (_vp * n)(*[int(p) for p in src_ptrs])
+        pitch = (ctypes.c_int64 * n)(*[int(p) for p in src_pitch])
+        fstr = (ctypes.c_int64 * n)(*[int(p) for p in src_frame_stride])
+        check(_lib.mcs_stitch_u8(self._h, ptrs, pitch, fstr, int(n_frames), _vp(int(dst_ptr)),
+                                 int(dst_pitch), int(dst_frame_stride), _vp(int(stream))),
+              "mcs_stitch_u8")
+
+    def owned_pixels(self, stream=0):
+        """Per-layer owned-pixel counts (cached)."""
+        if self._owned is None:
+            out = (ctypes.c_int64 * MCS_MAX_LAYERS)()
+            check(_lib.mcs_plan_owned_pixels(self._h, out, _vp(int(stream))), "mcs_plan_owned_pixels")
+            self._owned = [int(out[k]) for k in range(self.n_layers)]
+        return list(self._owned)
+
+    def algorithmic_bytes(self, stream=0):
+        """every output byte written once + one source
+        byte per non-background output byte."""
+        return self.out_w * self.out_h * self.channels + self.channels * sum(self.owned_pixels(stream))
+
+    def last_variant(self):
+        return int(_lib.mcs_plan_last_variant(self._h))

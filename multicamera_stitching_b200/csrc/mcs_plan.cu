@@ -1,0 +1,138 @@
+// Plan construction: host-side flattening checks, homography inversion, error plumbing.
+#include "mcs_common.h"
+
+#include <atomic>
+#include <new>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void mcs_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void mcs_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" const char* mcs_last_error(void) { return g_err; }
+extern "C" int mcs_abi_version(void) { return MCS_ABI_VERSION; }
+extern "C" int64_t mcs_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+// cv::invert for a 3x3 CV_64F matrix evaluates the determinant by cofactor expansion
+// along the first row, takes d = 1/det and multiplies every cofactor by d.  Reproducing
+// that association (and not, say, LAPACK's LU) matters: a 2e-13 difference in the
+// inverse already flips ~1 ppm of the 1/32-px coordinate buckets.
+bool mcs_invert3x3(const double* s, double* t) {
+    volatile double c00 = s[4] * s[8] - s[5] * s[7];
+    volatile double c01 = s[3] * s[8] - s[5] * s[6];
+    volatile double c02 = s[3] * s[7] - s[4] * s[6];
+    volatile double det = s[0] * c00 - s[1] * c01 + s[2] * c02;
+    if (det == 0.0) {
+        for (int i = 0; i < 9; ++i) t[i] = 0.0;  // cv::invert zero-fills a singular result
+        return false;
+    }
+    volatile double d = 1.0 / det;
+    t[0] = c00 * d;
+    t[1] = (s[2] * s[7] - s[1] * s[8]) * d;
+    t[2] = (s[1] * s[5] - s[2] * s[4]) * d;
+    t[3] = (s[5] * s[6] - s[3] * s[8]) * d;
+    t[4] = (s[0] * s[8] - s[2] * s[6]) * d;
+    t[5] = (s[2] * s[3] - s[0] * s[5]) * d;
+    t[6] = c02 * d;
+    t[7] = (s[1] * s[6] - s[0] * s[7]) * d;
+    t[8] = (s[0] * s[4] - s[1] * s[3]) * d;
+    return true;
+}
+
+extern "C" int mcs_plan_create(mcs_plan** out, int n_layers, int channels,
+                               const int32_t* layer_kind, const int32_t* src_hw,
+                               const double* fwd_h, const int32_t* origin_xy,
+                               const int32_t* rect_xyxy, int out_w, int out_h) {
+    MCS_CHECK_ARG(out != nullptr, "mcs_plan_create: out is NULL");
+    *out = nullptr;
+    MCS_CHECK_ARG(n_layers >= 1 && n_layers <= MCS_MAX_LAYERS,
+                  "mcs_plan_create: n_layers=%d outside 1..%d", n_layers, MCS_MAX_LAYERS);
+    MCS_CHECK_ARG(channels == 1 || channels == 3 || channels == 4,
+                  "mcs_plan_create: channels=%d (supported: 1, 3, 4)", channels);
+    MCS_CHECK_ARG(layer_kind && src_hw && origin_xy && rect_xyxy,
+                  "mcs_plan_create: NULL table pointer");
+    MCS_CHECK_ARG(out_w >= 0 && out_h >= 0 && out_w < (1 << 24) && out_h < (1 << 24),
+                  "mcs_plan_create: output size %dx%d out of range", out_w, out_h);
+
+    mcs_plan* p = new (std::nothrow) mcs_plan;
+    if (!p) {
+        mcs_set_error("mcs_plan_create: out of host memory");
+        return MCS_ERR_NOMEM;
+    }
+    memset(p, 0, sizeof(*p));
+    p->n_layers = n_layers;
+    p->channels = channels;
+    p->out_w = out_w;
+    p->out_h = out_h;
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e != cudaSuccess) {
+        mcs_set_error("mcs_plan_create: cudaGetDevice failed: %s", cudaGetErrorString(e));
+        delete p;
+        return MCS_ERR_CUDA;
+    }
+
+    for (int k = 0; k < n_layers; ++k) {
+        McsLayer& L = p->layers[k];
+        L.kind = layer_kind[k];
+        L.src_h = src_hw[2 * k];
+        L.src_w = src_hw[2 * k + 1];
+        L.ox = origin_xy[2 * k];
+        L.oy = origin_xy[2 * k + 1];
+        // clip the visible rectangle to the panorama
+        int x0 = rect_xyxy[4 * k], y0 = rect_xyxy[4 * k + 1];
+        int x1 = rect_xyxy[4 * k + 2], y1 = rect_xyxy[4 * k + 3];
+        x0 = x0 < 0 ? 0 : x0;
+        y0 = y0 < 0 ? 0 : y0;
+        x1 = x1 > out_w ? out_w : x1;
+        y1 = y1 > out_h ? out_h : y1;
+        if (x1 < x0) x1 = x0;
+        if (y1 < y0) y1 = y0;
+        L.rx0 = x0; L.ry0 = y0; L.rx1 = x1; L.ry1 = y1;
+        bool ok = (L.kind == MCS_LAYER_COPY || L.kind == MCS_LAYER_WARP) && L.src_h > 0 &&
+                  L.src_w > 0 && L.src_h < 32767 && L.src_w < 32767;  // cv2.remap's short-coordinate limit
+        // canvas-frame coordinates (x - ox, y - oy) must be non-negative inside the rectangle:
+        // the 64-column block split of the coordinate recipe is defined on x >= 0.
+        ok = ok && (x1 == x0 || y1 == y0 || (x0 >= L.ox && y0 >= L.oy));
+        if (ok && L.kind == MCS_LAYER_COPY) {
+            // a paste never reads outside the source
+            ok = (x1 == x0 || y1 == y0) ||
+                 (x1 - L.ox <= L.src_w && y1 - L.oy <= L.src_h);
+        }
+        if (!ok) {
+            mcs_set_error("mcs_plan_create: layer %d invalid (kind=%d src=%dx%d origin=(%d,%d) "
+                          "rect=[%d,%d,%d,%d))", k, L.kind, L.src_w, L.src_h, L.ox, L.oy, x0, y0, x1, y1);
+            delete p;
+            return MCS_ERR_INVALID;
+        }
+        if (L.kind == MCS_LAYER_WARP) {
+            if (!fwd_h) {
+                mcs_set_error("mcs_plan_create: fwd_h is NULL but layer %d is a WARP layer", k);
+                delete p;
+                return MCS_ERR_INVALID;
+            }
+            mcs_invert3x3(fwd_h + 9 * k, L.mi);  // singular -> all-zero inverse, as cv2 does
+            L.affine = (L.mi[6] == 0.0 && L.mi[7] == 0.0) ? 1 : 0;
+        } else {
+            L.mi[0] = L.mi[4] = L.mi[8] = 1.0;
+            L.affine = 1;
+        }
+    }
+    *out = p;
+    return MCS_OK;
+}
+
+extern "C" int mcs_plan_destroy(mcs_plan* plan) {
+    if (!plan) return MCS_OK;
+    delete plan;
+    return MCS_OK;
+}
+
+extern "C" int mcs_plan_last_variant(const mcs_plan* plan) { return plan ? plan->last_variant : 0; }

@@ -1,0 +1,264 @@
+// Fused warp + paste compositing kernels (sm_100a).
+//
+// One launch produces whole panoramas: every output pixel finds the innermost layer whose
+// rectangle contains it (the reference's repeated "warp A, then paste B over it",
+// StitcherClass.py:239-241 applied N-1 times by :131-136) and is either copied (camera 0)
+// or resampled with OpenCV's fixed-point bilinear recipe (cv2.warpPerspective, :239).
+//
+// Coordinate recipe (bit-exact with OpenCV's WarpPerspectiveInvoker):
+//   (xl, yl) = pixel in the layer's own canvas frame;  xb = xl & ~63, x1 = xl & 63
+//   X0 = (Mi0*xb + Mi1*yl) + Mi2  (likewise Y0, W0)          -- float64, round-to-nearest, NO fma
+//   W  = W0 + Mi6*x1 ; W = W ? 32/W : 0
+//   X  = rint(clamp((X0 + Mi0*x1) * W))   Y likewise          -- 1/32-px fixed point
+//   out = (sum_taps w*p + 16384) >> 15, w = 32 * {(32-ay)(32-ax), (32-ay)ax, ay(32-ax), ay*ax}
+// The float64 operations use the __d*_rn intrinsics, which the compiler never contracts.
+#include "mcs_common.h"
+
+struct LayerArgs {
+    McsLayer g;
+    const uint8_t* src;
+    long long pitch;
+    long long frame_stride;
+};
+
+struct StitchArgs {
+    LayerArgs L[MCS_MAX_LAYERS];
+    uint8_t* dst;
+    long long dst_pitch;
+    long long dst_frame_stride;
+    int n_layers;
+    int out_w, out_h;
+    int n_frames;
+};
+
+// --------------------------------------------------------------------------------------------
+// per-pixel building blocks
+
+struct RowBlock {  // X0, Y0, W0 of one (layer, row, 64-column block)
+    double X0, Y0, W0;
+};
+
+__device__ __forceinline__ RowBlock row_block(const double* __restrict__ mi, int xb, int yl) {
+    const double xbd = (double)xb, yd = (double)yl;
+    RowBlock r;
+    r.X0 = __dadd_rn(__dadd_rn(__dmul_rn(mi[0], xbd), __dmul_rn(mi[1], yd)), mi[2]);
+    r.Y0 = __dadd_rn(__dadd_rn(__dmul_rn(mi[3], xbd), __dmul_rn(mi[4], yd)), mi[5]);
+    r.W0 = __dadd_rn(__dadd_rn(__dmul_rn(mi[6], xbd), __dmul_rn(mi[7], yd)), mi[8]);
+    return r;
+}
+
+// 1/32-px source coordinates of column x1 (0..63) of a row block.
+__device__ __forceinline__ void fixed_coords(const double* __restrict__ mi, const RowBlock& rb,
+                                             int x1, int& X, int& Y) {
+    const double x1d = (double)x1;
+    double W = __dadd_rn(rb.W0, __dmul_rn(mi[6], x1d));
+    const bool wz = (W == 0.0);
+    W = __ddiv_rn(32.0, W);
+    const double fX = __dmul_rn(__dadd_rn(rb.X0, __dmul_rn(mi[0], x1d)), W);
+    const double fY = __dmul_rn(__dadd_rn(rb.Y0, __dmul_rn(mi[3], x1d)), W);
+    // cvt.rni.s32.f64 saturates to [INT_MIN, INT_MAX] exactly like the reference's clamp + cvRound
+    X = wz ? 0 : __double2int_rn(fX);
+    Y = wz ? 0 : __double2int_rn(fY);
+}
+
+template <int C>
+__device__ __forceinline__ void load_px(const uint8_t* __restrict__ p, int (&v)[C]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = __ldg(p + c);
+}
+
+// Fixed-point bilinear sample of `src` at (X, Y) in 1/32 px.  `touched` reports whether any tap
+// was inside the source (used by the ownership statistics).
+template <int C>
+__device__ __forceinline__ bool sample_u8(const uint8_t* __restrict__ src, long long pitch, int src_w,
+                                          int src_h, int X, int Y, int (&out)[C]) {
+    int sx = X >> 5, sy = Y >> 5;
+    // saturate_cast<short> of the integer part: anything clamped is outside any legal source anyway
+    sx = max(-32768, min(32767, sx));
+    sy = max(-32768, min(32767, sy));
+    const int ax = X & 31, ay = Y & 31;
+    const bool x0in = (unsigned)sx < (unsigned)src_w, x1in = (unsigned)(sx + 1) < (unsigned)src_w;
+    const bool y0in = (unsigned)sy < (unsigned)src_h, y1in = (unsigned)(sy + 1) < (unsigned)src_h;
+    int p00[C], p01[C], p10[C], p11[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) p00[c] = p01[c] = p10[c] = p11[c] = 0;
+    const uint8_t* r0 = src + (long long)sy * pitch + (long long)sx * C;
+    const uint8_t* r1 = r0 + pitch;
+    if (y0in && x0in) load_px<C>(r0, p00);
+    if (y0in && x1in) load_px<C>(r0 + C, p01);
+    if (y1in && x0in) load_px<C>(r1, p10);
+    if (y1in && x1in) load_px<C>(r1 + C, p11);
+    const int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32;
+    const int w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        out[c] = (w00 * p00[c] + w01 * p01[c] + w10 * p10[c] + w11 * p11[c] + 16384) >> 15;
+    return (x0in || x1in) && (y0in || y1in);
+}
+
+__device__ __forceinline__ int find_owner(const StitchArgs& a, int x, int y) {
+    for (int k = 0; k < a.n_layers; ++k) {
+        const McsLayer& g = a.L[k].g;
+        if (x >= g.rx0 && x < g.rx1 && y >= g.ry0 && y < g.ry1) return k;
+    }
+    return -1;
+}
+
+// --------------------------------------------------------------------------------------------
+// Variant 1 ("gather"): one thread per 4 consecutive output pixels, source taps fetched straight
+// from global memory.  Handles every layout (any pitch / alignment / homography); it is the
+// fallback of the tiled variant, never of a CPU path.
+//
+// STATS = true turns the kernel into the ownership counter behind mcs_plan_owned_pixels.
+template <int C, bool STATS>
+__global__ void __launch_bounds__(256)
+mcs_stitch_gather_kernel(const __grid_constant__ StitchArgs a, unsigned long long* __restrict__ owned) {
+    const int x_first = blockIdx.x * MCS_TILE_W + threadIdx.x * 4;
+    const int y = blockIdx.y * MCS_TILE_H + threadIdx.y;
+    if (y >= a.out_h || x_first >= a.out_w) return;
+    const int frame = blockIdx.z;
+
+    int prev_owner = -2, prev_xb = 0;
+    RowBlock rb = {0.0, 0.0, 0.0};
+    uint8_t px[4 * C];
+    const int n_px = min(4, a.out_w - x_first);
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = 0;
+        const int x = x_first + i;
+        if (i < n_px) {
+            const int k = find_owner(a, x, y);
+            if (k >= 0) {
+                const LayerArgs& L = a.L[k];
+                const int xl = x - L.g.ox, yl = y - L.g.oy;
+                const uint8_t* src = L.src + (long long)frame * L.frame_stride;
+                bool touched = true;
+                if (L.g.kind == MCS_LAYER_COPY) {
+                    if (!STATS) load_px<C>(src + (long long)yl * L.pitch + (long long)xl * C, v);
+                } else {
+                    const int xb = xl & ~63;
+                    if (k != prev_owner || xb != prev_xb) {
+                        rb = row_block(L.g.mi, xb, yl);
+                        prev_owner = k;
+                        prev_xb = xb;
+                    }
+                    int X, Y;
+                    fixed_coords(L.g.mi, rb, xl & 63, X, Y);
+                    if (STATS) {
+                        const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+                        touched = ((unsigned)sx < (unsigned)L.g.src_w || (unsigned)(sx + 1) < (unsigned)L.g.src_w) &&
+                                  ((unsigned)sy < (unsigned)L.g.src_h || (unsigned)(sy + 1) < (unsigned)L.g.src_h);
+                    } else {
+                        sample_u8<C>(src, L.pitch, L.g.src_w, L.g.src_h, X, Y, v);
+                    }
+                }
+                if (STATS && touched) atomicAdd(owned + k, 1ULL);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) px[i * C + c] = (uint8_t)v[c];
+    }
+    if (STATS) return;
+
+    uint8_t* out = a.dst + (long long)frame * a.dst_frame_stride + (long long)y * a.dst_pitch +
+                   (long long)x_first * C;
+    const bool aligned4 = ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
+    if (n_px == 4 && aligned4) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+        for (int wd = 0; wd < C; ++wd)
+            o32[wd] = (uint32_t)px[4 * wd] | ((uint32_t)px[4 * wd + 1] << 8) |
+                      ((uint32_t)px[4 * wd + 2] << 16) | ((uint32_t)px[4 * wd + 3] << 24);
+    } else {
+        for (int b = 0; b < n_px * C; ++b) out[b] = px[b];
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+static int fill_args(const mcs_plan* plan, StitchArgs& a, const uint8_t* const* src,
+                     const int64_t* src_pitch, const int64_t* src_frame_stride, int n_frames,
+                     uint8_t* dst, int64_t dst_pitch, int64_t dst_frame_stride) {
+    a.n_layers = plan->n_layers;
+    a.out_w = plan->out_w;
+    a.out_h = plan->out_h;
+    a.n_frames = n_frames;
+    a.dst = dst;
+    a.dst_pitch = dst_pitch;
+    a.dst_frame_stride = dst_frame_stride;
+    for (int k = 0; k < plan->n_layers; ++k) {
+        a.L[k].g = plan->layers[k];
+        a.L[k].src = src ? src[k] : nullptr;
+        a.L[k].pitch = src_pitch ? src_pitch[k] : 0;
+        a.L[k].frame_stride = (src_frame_stride && n_frames > 1) ? src_frame_stride[k] : 0;
+    }
+    return MCS_OK;
+}
+
+template <bool STATS>
+static cudaError_t launch_gather(const mcs_plan* plan, const StitchArgs& a, unsigned long long* owned,
+                                 cudaStream_t stream) {
+    dim3 block(MCS_TILE_W / 4, MCS_TILE_H, 1);
+    dim3 grid((plan->out_w + MCS_TILE_W - 1) / MCS_TILE_W, (plan->out_h + MCS_TILE_H - 1) / MCS_TILE_H,
+              a.n_frames);
+    switch (plan->channels) {
+        case 1: mcs_stitch_gather_kernel<1, STATS><<<grid, block, 0, stream>>>(a, owned); break;
+        case 3: mcs_stitch_gather_kernel<3, STATS><<<grid, block, 0, stream>>>(a, owned); break;
+        default: mcs_stitch_gather_kernel<4, STATS><<<grid, block, 0, stream>>>(a, owned); break;
+    }
+    mcs_count_launch(1);
+    return cudaGetLastError();
+}
+
+extern "C" int mcs_stitch_u8(const mcs_plan* plan, const uint8_t* const* src,
+                             const int64_t* src_pitch_bytes, const int64_t* src_frame_stride,
+                             int n_frames, uint8_t* dst, int64_t dst_pitch_bytes,
+                             int64_t dst_frame_stride, void* cuda_stream) {
+    MCS_CHECK_ARG(plan != nullptr, "mcs_stitch_u8: plan is NULL");
+    MCS_CHECK_ARG(src && src_pitch_bytes, "mcs_stitch_u8: NULL source table");
+    MCS_CHECK_ARG(n_frames >= 0 && n_frames <= 65535, "mcs_stitch_u8: n_frames=%d outside 0..65535", n_frames);
+    if (n_frames == 0 || plan->out_w == 0 || plan->out_h == 0) return MCS_OK;
+    MCS_CHECK_ARG(dst != nullptr, "mcs_stitch_u8: dst is NULL");
+    MCS_CHECK_ARG(dst_pitch_bytes >= (int64_t)plan->out_w * plan->channels,
+                  "mcs_stitch_u8: dst pitch %lld < row bytes %lld", (long long)dst_pitch_bytes,
+                  (long long)plan->out_w * plan->channels);
+    MCS_CHECK_ARG(n_frames == 1 || src_frame_stride != nullptr, "mcs_stitch_u8: NULL frame strides");
+    for (int k = 0; k < plan->n_layers; ++k) {
+        MCS_CHECK_ARG(src[k] != nullptr, "mcs_stitch_u8: source %d is NULL", k);
+        MCS_CHECK_ARG(src_pitch_bytes[k] >= (int64_t)plan->layers[k].src_w * plan->channels,
+                      "mcs_stitch_u8: source %d pitch %lld < row bytes", k, (long long)src_pitch_bytes[k]);
+    }
+    StitchArgs a;
+    fill_args(plan, a, src, src_pitch_bytes, src_frame_stride, n_frames, dst, dst_pitch_bytes,
+              dst_frame_stride);
+    MCS_CHECK_CUDA(launch_gather<false>(plan, a, nullptr, (cudaStream_t)cuda_stream));
+    const_cast<mcs_plan*>(plan)->last_variant = 1;
+    return MCS_OK;
+}
+
+extern "C" int mcs_plan_owned_pixels(const mcs_plan* plan, int64_t* owned_host, void* cuda_stream) {
+    MCS_CHECK_ARG(plan != nullptr && owned_host != nullptr, "mcs_plan_owned_pixels: NULL argument");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    unsigned long long* d = nullptr;
+    MCS_CHECK_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * MCS_MAX_LAYERS));
+    int rc = MCS_OK;
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long) * MCS_MAX_LAYERS, stream);
+    if (e == cudaSuccess && plan->out_w > 0 && plan->out_h > 0) {
+        StitchArgs a;
+        fill_args(plan, a, nullptr, nullptr, nullptr, 1, nullptr, 0, 0);
+        e = launch_gather<true>(plan, a, d, stream);
+    }
+    unsigned long long h[MCS_MAX_LAYERS];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        mcs_set_error("mcs_plan_owned_pixels: %s", cudaGetErrorString(e));
+        rc = MCS_ERR_CUDA;
+    } else {
+        for (int k = 0; k < plan->n_layers; ++k) owned_host[k] = (int64_t)h[k];
+    }
+    cudaFree(d);
+    return rc;
+}

@@ -1,0 +1,147 @@
+"""Host side of the fused compositing path: plan cache, device staging and the
+calls into ``libmcs_b200.so``.
+
+PyTorch is used here only as plumbing - device memory, pinned host memory,
+streams.  All arithmetic happens in the sm_100a kernels behind the C ABI; if
+the library or a CUDA device is missing the calls raise, there is no CPU path.
+"""
+import numpy as np
+import torch
+
+from . import _cabi
+from .plan import flatten_chain, plan_tables, stage_signature
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class CompiledPlan(object):
+    """A flattened chain plus its ``mcs_plan`` on one device."""
+
+    def __init__(self, flat, device):
+        self.flat = flat
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            kind, src_hw, fwd, origin, rect = plan_tables(flat)
+            self.handle = _cabi.Plan(kind, src_hw, fwd, origin, rect, flat.out_w, flat.out_h, flat.channels)
+        self.cams = [l.cam for l in flat.layers]
+        self.out_w, self.out_h, self.channels = flat.out_w, flat.out_h, flat.channels
+
+    # ---- geometry helpers -------------------------------------------------
+    def out_shape(self, n_frames=None):
+        s = (self.out_h, self.out_w) + ((self.channels,) if self.flat.ndim == 3 else ())
+        return s if n_frames is None else (n_frames,) + s
+
+    def algorithmic_bytes(self):
+        with torch.cuda.device(self.device):
+            return self.handle.algorithmic_bytes(torch.cuda.current_stream().cuda_stream)
+
+    def owned_pixels(self):
+        with torch.cuda.device(self.device):
+            return self.handle.owned_pixels(torch.cuda.current_stream().cuda_stream)
+
+    # ---- launch -----------------------------------------------------------
+    def _describe(self, t, batched):
+        """(data_ptr, pitch_bytes, frame_stride_bytes) of a uint8 CUDA tensor
+        holding [F,]H,W[,C] frames with dense pixels."""
+        if t.dtype != torch.uint8 or not t.is_cuda:
+            raise TypeError("frames must be uint8 CUDA tensors, got %s on %s" % (t.dtype, t.device))
+        nd = self.flat.ndim + (1 if batched else 0)
+        if t.dim() != nd:
+            raise ValueError("expected a %d-D frame tensor, got shape %r" % (nd, tuple(t.shape)))
+        st = t.stride()
+        if self.flat.ndim == 3:
+            dense = st[-1] == 1 and st[-2] == self.channels
+            pitch = st[-3]
+        else:
+            dense = st[-1] == 1
+            pitch = st[-2]
+        if not dense:
+            raise ValueError("frame pixels must be densely packed (strides %r)" % (st,))
+        return t.data_ptr(), pitch, (st[0] if batched else 0)
+
+    def new_output(self, n_frames=None, pitch_align=1):
+        """Uninitialised output tensor (every byte of it is written by the
+        kernel).  With ``pitch_align`` > 1 rows are padded and a strided view
+        is returned."""
+        F = 1 if n_frames is None else n_frames
+        row = self.out_w * self.channels
+        pitch = _round_up(max(row, 1), pitch_align)
+        buf = torch.empty((F, self.out_h, pitch), dtype=torch.uint8, device=self.device)
+        if self.flat.ndim == 3:
+            view = torch.as_strided(buf, (F, self.out_h, self.out_w, self.channels),
+                                    (self.out_h * pitch, pitch, self.channels, 1))
+        else:
+            view = torch.as_strided(buf, (F, self.out_h, self.out_w), (self.out_h * pitch, pitch, 1))
+        return view if n_frames is not None else view[0]
+
+    def run(self, frames_by_cam, out=None, n_frames=None, stream=None):
+        """Composite.  ``frames_by_cam[c]`` is the CUDA tensor of camera ``c``
+        ([H,W,C] or, when ``n_frames`` is given, [F,H,W,C]).  Returns ``out``."""
+        batched = n_frames is not None
+        F = n_frames if batched else 1
+        if out is None:
+            out = self.new_output(n_frames)
+        if tuple(out.shape) != self.out_shape(n_frames):
+            raise ValueError("output shape %r != %r" % (tuple(out.shape), self.out_shape(n_frames)))
+        ptrs, pitches, fstrides = [], [], []
+        for l in self.flat.layers:
+            t = frames_by_cam[l.cam]
+            want = ((F,) if batched else ()) + tuple(l.src_hw) + ((self.channels,) if self.flat.ndim == 3 else ())
+            if tuple(t.shape) != want:
+                raise ValueError("camera %d: frame shape %r != %r" % (l.cam, tuple(t.shape), want))
+            p, pitch, fs = self._describe(t, batched)
+            ptrs.append(p)
+            pitches.append(pitch)
+            fstrides.append(fs)
+        dp, dpitch, dfs = self._describe(out, batched)
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream() if stream is None else stream
+            self.handle.stitch(ptrs, pitches, fstrides, F, dp, dpitch, dfs, s.cuda_stream)
+        return out
+
+
+class CompositeEngine(object):
+    """Plan cache + host<->device staging for one ``Stitcher``."""
+
+    def __init__(self, device=None):
+        self._device = device
+        self._plans = {}
+        self._staging = {}
+
+    @property
+    def device(self):
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise _cabi.McsError("no CUDA device: the compositing path has no CPU fallback")
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        return torch.device(self._device)
+
+    def plan_for(self, stages, cam_shapes, device=None):
+        """Compiled plan for this chain state and these frame shapes, or None
+        when no stage is calibrated."""
+        device = torch.device(device) if device is not None else self.device
+        key = (str(device), tuple(tuple(int(v) for v in s) for s in cam_shapes),
+               tuple(stage_signature(st) for st in stages))
+        if key not in self._plans:
+            flat = flatten_chain(stages, cam_shapes)
+            if len(self._plans) > 8:
+                self._plans.clear()
+            self._plans[key] = CompiledPlan(flat, device) if flat is not None else None
+        return self._plans[key]
+
+    def upload(self, cam, arr, device):
+        """Host frame -> (reused) device tensor on the current stream."""
+        t = torch.from_numpy(np.ascontiguousarray(arr)) if isinstance(arr, np.ndarray) else arr.contiguous()
+        key = (cam, tuple(t.shape), str(device))
+        buf = self._staging.get(key)
+        if buf is None:
+            buf = torch.empty(t.shape, dtype=torch.uint8, device=device)
+            self._staging[key] = buf
+        buf.copy_(t, non_blocking=True)
+        return buf
+
+    def reset(self):
+        self._plans.clear()
+        self._staging.clear()

@@ -1,0 +1,131 @@
+"""Flatten a calibrated stitcher chain into the layer table of one compositing
+plan (host logic, no GPU needed).
+
+The reference composites with N-1 sequential stages, each of which warps the
+next camera into a fresh canvas and pastes the running canvas over it
+(StitcherClass.py:131-136, :237-251).  Because every paste is an axis-aligned
+rectangle overwrite, the final value of an output pixel is decided by the
+*innermost* pasted rectangle that contains it.  ``flatten_chain`` walks the
+stage states once and produces, for every camera, its rectangle and canvas
+origin in final-panorama coordinates; ``mcs_plan_create`` (include/mcs.h) turns
+that table into the plan the fused kernel executes.
+"""
+from collections import namedtuple
+
+import numpy as np
+
+LAYER_COPY = 0
+LAYER_WARP = 1
+
+Layer = namedtuple("Layer", "cam kind H ox oy rect src_hw")
+FlatPlan = namedtuple("FlatPlan", "layers out_w out_h channels ndim")
+
+
+class PlanUnsupported(Exception):
+    """The chain needs something the fused one-pass plan cannot express."""
+
+
+def _field(st, name):
+    return st[name] if isinstance(st, dict) else getattr(st, name)
+
+
+def _numpy_window(start, stop, size):
+    """Start/stop of ``a[start:stop]`` on an axis of length ``size`` with
+    Python's slice semantics (negative indices wrap, out-of-range clamps)."""
+    lo, hi, _ = slice(start, stop).indices(size)
+    return lo, max(lo, hi)
+
+
+def stage_signature(st):
+    """Hashable snapshot of everything of a stage that shapes the plan."""
+    H = _field(st, "cachedAH")
+    if H is None:
+        return None
+    Bpts = _field(st, "Bpts")
+    xl, yl = _field(st, "x_limits"), _field(st, "y_limits")
+    return (np.asarray(H, dtype=np.float64).tobytes(),
+            int(Bpts[0][0]), int(Bpts[0][1]),
+            tuple(int(v) for v in _field(st, "ABSize")),
+            tuple(_field(st, "AimgSize")), tuple(_field(st, "BimgSize")),
+            bool(_field(st, "super_mode")),
+            tuple(xl) if xl is not None else None, tuple(yl) if yl is not None else None)
+
+
+def flatten_chain(stages, cam_shapes):
+    """``stages``: the N-1 ``StitcherBase`` objects (or dicts with the same
+    field names) in chain order.  ``cam_shapes``: ``ndarray.shape`` of the N
+    camera frames in label order.  Returns a :class:`FlatPlan` whose layers are
+    ordered innermost first, or ``None`` when no stage is calibrated (the
+    reference then hands the first frame straight through,
+    StitcherClass.py:255-256)."""
+    shape0 = tuple(int(v) for v in cam_shapes[0])
+    if len(shape0) not in (2, 3):
+        raise PlanUnsupported("frames must be HxW or HxWxC, got shape %r" % (shape0,))
+    ndim = len(shape0)
+    channels = 1 if ndim == 2 else shape0[2]
+    tail = shape0[2:]
+    layers = [Layer(0, LAYER_COPY, None, 0, 0, (0, 0, shape0[1], shape0[0]), (shape0[0], shape0[1]))]
+    cur_shape = shape0
+    any_calibrated = False
+
+    for s, st in enumerate(stages):
+        H = _field(st, "cachedAH")
+        if H is None:
+            continue  # uncalibrated stage: the running canvas passes through
+        any_calibrated = True
+        shapeA = tuple(int(v) for v in cam_shapes[s + 1])
+        if cur_shape != tuple(_field(st, "BimgSize")):
+            raise PlanUnsupported(
+                "stage %d: running canvas has shape %r but was calibrated for %r (resizing a "
+                "composited canvas is not expressible in one pass)" % (s, cur_shape, tuple(_field(st, "BimgSize"))))
+        if shapeA != tuple(_field(st, "AimgSize")):
+            raise PlanUnsupported("stage %d: frame shape %r != calibrated %r"
+                                  % (s, shapeA, tuple(_field(st, "AimgSize"))))
+        if shapeA[2:] != tail:
+            raise PlanUnsupported("stage %d: channel layout %r differs from %r" % (s, shapeA[2:], tail))
+        Bpts = _field(st, "Bpts")
+        bx, by = int(Bpts[0][0]), int(Bpts[0][1])
+        W, Hh = int(_field(st, "ABSize")[0]), int(_field(st, "ABSize")[1])
+        hB, wB = cur_shape[0], cur_shape[1]
+        # dst[by:by+hB, bx:bx+wB] = imageB  (numpy raises if the window is not hB x wB)
+        y0, y1 = _numpy_window(by, by + hB, Hh)
+        x0, x1 = _numpy_window(bx, bx + wB, W)
+        if (y1 - y0, x1 - x0) != (hB, wB):
+            raise ValueError("could not broadcast input array from shape %r into shape %r"
+                             % ((hB, wB) + tail, (y1 - y0, x1 - x0) + tail))
+        layers = [l._replace(ox=l.ox + x0, oy=l.oy + y0,
+                             rect=(l.rect[0] + x0, l.rect[1] + y0, l.rect[2] + x0, l.rect[3] + y0))
+                  for l in layers]
+        layers.append(Layer(s + 1, LAYER_WARP, np.array(H, dtype=np.float64).reshape(3, 3), 0, 0,
+                            (0, 0, W, Hh), (shapeA[0], shapeA[1])))
+        cw, ch = W, Hh
+        if _field(st, "super_mode"):
+            yl, xl = _field(st, "y_limits"), _field(st, "x_limits")
+            cy0, cy1 = _numpy_window(yl[0], yl[1], Hh)
+            cx0, cx1 = _numpy_window(xl[0], xl[1], W)
+            cw, ch = cx1 - cx0, cy1 - cy0
+            clipped = []
+            for l in layers:
+                r = (max(0, l.rect[0] - cx0), max(0, l.rect[1] - cy0),
+                     min(cw, l.rect[2] - cx0), min(ch, l.rect[3] - cy0))
+                r = (r[0], r[1], max(r[0], r[2]), max(r[1], r[3]))
+                clipped.append(l._replace(ox=l.ox - cx0, oy=l.oy - cy0, rect=r))
+            layers = clipped
+        cur_shape = (ch, cw) + tail
+
+    if not any_calibrated:
+        return None
+    return FlatPlan(layers, cur_shape[1], cur_shape[0], channels, ndim)
+
+
+def plan_tables(flat):
+    """Arrays in the layout ``mcs_plan_create`` takes."""
+    n = len(flat.layers)
+    kind = np.array([l.kind for l in flat.layers], dtype=np.int32)
+    src_hw = np.array([l.src_hw for l in flat.layers], dtype=np.int32).reshape(n, 2)
+    origin = np.array([(l.ox, l.oy) for l in flat.layers], dtype=np.int32).reshape(n, 2)
+    rect = np.array([l.rect for l in flat.layers], dtype=np.int32).reshape(n, 4)
+    fwd = np.zeros((n, 9), dtype=np.float64)
+    for i, l in enumerate(flat.layers):
+        fwd[i] = np.eye(3).ravel() if l.H is None else np.asarray(l.H, dtype=np.float64).ravel()
+    return kind, src_hw, fwd, origin, rect

@@ -1,0 +1,98 @@
+"""Recorded-sequence driver: frame-range sharding across GPUs and the pipelined
+host -> device -> kernel -> host path.
+
+Every panorama depends only on its own N frames and the fixed calibration
+(``Stitcher.stitch`` keeps no state between calls, reference
+StitcherClass.py:114-136), so a sequence shards by contiguous frame range with
+no data-path collective: each process (one per GPU) composites its range and
+only its own output goes back to the host (SURVEY.md section 8 row e).
+"""
+import torch
+
+
+def shard_range(n_frames, world_size, rank):
+    """Contiguous frame range ``[lo, hi)`` of ``rank``: sizes differ by at most
+    one, earlier ranks take the remainder, ranges tile ``[0, n_frames)``."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank %d / world size %d" % (rank, world_size))
+    base, rem = divmod(int(n_frames), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pinned_like(shape, dtype=torch.uint8):
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+class SequencePipeline(object):
+    """Composite a host-resident sequence chunk by chunk with copies and
+    kernels overlapped on three streams (H2D, compute, D2H) and ``depth``
+    device-side slots.
+
+    ``run(host_frames, host_out)``: ``host_frames[label]`` is a pinned uint8
+    tensor ``[F, H, W, C]``, ``host_out`` a pinned ``[F, H_out, W_out, C]``.
+    """
+
+    def __init__(self, stitcher, img_shapes, device, chunk=4, depth=2):
+        self.stitcher = stitcher
+        self.device = torch.device(device)
+        self.labels = list(stitcher.img_labels)
+        self.plan = stitcher.plan(img_shapes, self.device)
+        if self.plan is None:
+            raise ValueError("stitcher is not calibrated")
+        self.chunk = int(chunk)
+        self.depth = int(depth)
+        with torch.cuda.device(self.device):
+            self.s_in = torch.cuda.Stream()
+            self.s_k = torch.cuda.Stream()
+            self.s_out = torch.cuda.Stream()
+            self.slots = []
+            for _ in range(self.depth):
+                src = [torch.empty((self.chunk,) + tuple(s), dtype=torch.uint8, device=self.device)
+                       for s in img_shapes]
+                dst = self.plan.new_output(self.chunk)
+                self.slots.append(dict(src=src, dst=dst, ev_in=torch.cuda.Event(), ev_k=torch.cuda.Event(),
+                                       ev_out=torch.cuda.Event(), used=False))
+
+    def bytes_per_frame(self):
+        h2d = sum(int(s["src"][c][0].numel()) for s in self.slots[:1] for c in range(len(self.labels)))
+        d2h = int(self.slots[0]["dst"][0].numel())
+        return h2d, d2h
+
+    def run(self, host_frames, host_out, lo=0, hi=None):
+        """Composite frames ``[lo, hi)`` of the host sequence into
+        ``host_out[lo:hi]``; returns the number of panoramas produced.  The
+        call returns after the last device->host copy has completed."""
+        F = int(host_out.shape[0])
+        hi = F if hi is None else hi
+        with torch.cuda.device(self.device):
+            start = torch.cuda.current_stream()
+            for s in (self.s_in, self.s_k, self.s_out):
+                s.wait_stream(start)
+            i = 0
+            for f0 in range(lo, hi, self.chunk):
+                n = min(self.chunk, hi - f0)
+                slot = self.slots[i % self.depth]
+                i += 1
+                with torch.cuda.stream(self.s_in):
+                    if slot["used"]:
+                        self.s_in.wait_event(slot["ev_k"])      # previous kernel done reading the slot
+                    for c, label in enumerate(self.labels):
+                        slot["src"][c][:n].copy_(host_frames[label][f0:f0 + n], non_blocking=True)
+                    slot["ev_in"].record(self.s_in)
+                with torch.cuda.stream(self.s_k):
+                    self.s_k.wait_event(slot["ev_in"])
+                    if slot["used"]:
+                        self.s_k.wait_event(slot["ev_out"])     # previous D2H done reading dst
+                    self.plan.run([t[:n] for t in slot["src"]], out=slot["dst"][:n], n_frames=n,
+                                  stream=self.s_k)
+                    slot["ev_k"].record(self.s_k)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(slot["ev_k"])
+                    host_out[f0:f0 + n].copy_(slot["dst"][:n], non_blocking=True)
+                    slot["ev_out"].record(self.s_out)
+                slot["used"] = True
+            start.wait_stream(self.s_out)
+            start.wait_stream(self.s_k)
+            start.wait_stream(self.s_in)
+        return hi - lo
