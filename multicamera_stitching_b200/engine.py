@@ -120,12 +120,15 @@ class CompositeEngine(object):
 
     def plan_for(self, stages, cam_shapes, device=None):
         """Compiled plan for this chain state and these frame shapes, or None
-        when no stage is calibrated."""
+        when no stage is calibrated (decided on the host, no device needed)."""
+        shapes = tuple(tuple(int(v) for v in s) for s in cam_shapes)
+        sig = tuple(stage_signature(st) for st in stages)
+        if all(s is None for s in sig):
+            return None
         device = torch.device(device) if device is not None else self.device
-        key = (str(device), tuple(tuple(int(v) for v in s) for s in cam_shapes),
-               tuple(stage_signature(st) for st in stages))
+        key = (str(device), shapes, sig)
         if key not in self._plans:
-            flat = flatten_chain(stages, cam_shapes)
+            flat = flatten_chain(stages, shapes)
             if len(self._plans) > 8:
                 self._plans.clear()
             self._plans[key] = CompiledPlan(flat, device) if flat is not None else None
