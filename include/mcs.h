@@ -119,6 +119,15 @@ int mcs_stitch_u8(const mcs_plan* plan, const uint8_t* const* src,
  * (diagnostics for tests / bench): 0 = none yet, 1 = gather, 2 = tiled. */
 int mcs_plan_last_variant(const mcs_plan* plan);
 
+/* Pin the kernel variant of a plan: 0 = automatic (tiled when the plan and the buffers allow
+ * it, else gather), 1 = gather, 2 = tiled (mcs_stitch_u8 then fails with MCS_ERR_UNSUPPORTED
+ * instead of switching).  For tests and benchmarks. */
+int mcs_plan_force_variant(mcs_plan* plan, int variant);
+
+/* "" when the tiled (TMA-staged) variant is available for this plan, else the reason it is
+ * not (the gather variant then serves every call). */
+const char* mcs_plan_tiled_status(const mcs_plan* plan);
+
 /* Number of kernels this library has launched in the calling process. */
 int64_t mcs_launch_count(void);
 

@@ -20,7 +20,8 @@ ABI_VERSION = 1
 # every symbol include/mcs.h declares
 EXPORTS = (
     "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_destroy",
-    "mcs_plan_owned_pixels", "mcs_stitch_u8", "mcs_plan_last_variant", "mcs_launch_count",
+    "mcs_plan_owned_pixels", "mcs_stitch_u8", "mcs_plan_last_variant", "mcs_plan_force_variant",
+    "mcs_plan_tiled_status", "mcs_launch_count",
     "mcs_match_hamming_top2", "mcs_ransac_homography",
 )
 
@@ -70,6 +71,10 @@ def load(build_if_missing=False):
                                   ctypes.c_int64, ctypes.c_int64, _vp]
     lib.mcs_plan_last_variant.restype = ctypes.c_int
     lib.mcs_plan_last_variant.argtypes = [_vp]
+    lib.mcs_plan_force_variant.restype = ctypes.c_int
+    lib.mcs_plan_force_variant.argtypes = [_vp, ctypes.c_int]
+    lib.mcs_plan_tiled_status.restype = ctypes.c_char_p
+    lib.mcs_plan_tiled_status.argtypes = [_vp]
     lib.mcs_launch_count.restype = ctypes.c_int64
     lib.mcs_launch_count.argtypes = []
     lib.mcs_match_hamming_top2.restype = ctypes.c_int
@@ -152,3 +157,11 @@ class Plan(object):
 
     def last_variant(self):
         return int(_lib.mcs_plan_last_variant(self._h))
+
+    def force_variant(self, variant):
+        """0 = automatic, 1 = gather kernel, 2 = tiled (TMA-staged) kernel."""
+        check(_lib.mcs_plan_force_variant(self._h, int(variant)), "mcs_plan_force_variant")
+
+    def tiled_status(self):
+        """'' when the tiled variant is available, else why it is not."""
+        return _lib.mcs_plan_tiled_status(self._h).decode(errors="replace")

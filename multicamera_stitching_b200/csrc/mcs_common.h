@@ -33,34 +33,48 @@ void mcs_count_launch(int n);
     } while (0)
 
 // ---- compositing plan -----------------------------------------------------
-// One camera of the panorama, in the form the kernels consume.
+// One camera of the panorama, in the form the kernels consume (host copy in the plan, device
+// copy in plan->d_layers).
 struct McsLayer {
-    double mi[9];        // inverse homography (output-canvas frame -> source), cv::invert closed form
+    double mi[9];            // inverse homography (layer canvas frame -> source), cv::invert closed form
     int rx0, ry0, rx1, ry1;  // visible rectangle, output coordinates, half open
-    int ox, oy;          // origin of the layer's canvas frame in output coordinates
+    int ox, oy;              // origin of the layer's canvas frame in output coordinates
     int src_w, src_h;
-    int kind;            // MCS_LAYER_*
-    int affine;          // mi[6] == mi[7] == 0: the perspective divide is a per-plan constant
+    int kind;                // MCS_LAYER_*
+    int affine;              // mi[6] == mi[7] == 0
+    int bw4;                 // tiled variant: staged box width in 4-byte words (multiple of 4, <= 256)
+    int bh;                  // tiled variant: staged box height in rows (<= 256)
 };
 
-// Work item of the tiled kernel: one 64 x 16 output tile (host-built at plan creation).
+// Work item of the tiled kernel: the part of one 128 x 16 cell of a layer's own canvas grid that
+// the layer owns.  Cells are aligned to the layer frame (cell column 0 sits at canvas x = 128*i),
+// so a cell spans exactly two of OpenCV's 64-column coordinate blocks.
 struct McsTile {
-    int x0, y0;          // output coordinates of the tile origin
-    short w, h;          // valid extent (clipped at the panorama border)
-    short layer;         // owner layer, or -1 = background, -2 = mixed ownership
-    short cls;           // MCS_TILE_*
-    int sx0, sy0;        // source-pixel origin of the staged box (WARP_STAGED)
-    short sw, sh;        // staged box extent in source pixels
-    int pad;
+    int cx0;         // output x of cell column 0
+    int y0;          // output y of the first row
+    short c0, c1;    // owned cell columns [c0, c1), 0 <= c0 < c1 <= 128
+    short h;         // rows, 1..16
+    short layer;     // owner layer, -1 for background
+    short cls;       // MCS_TILE_*
+    short flags;
+    int bx;          // staged box origin: 4-byte word index within the source row (may be negative)
+    int by;          // staged box origin: source row (may be negative)
+    int reserved;
 };
+static_assert(sizeof(McsTile) == 32, "McsTile must stay 32 bytes");
 
+#define MCS_CELL_W 128
+#define MCS_CELL_H 16
+
+#define MCS_TILE_ZERO 0   // nothing to sample: write zeros
+#define MCS_TILE_COPY 1   // verbatim paste of the source window
+#define MCS_TILE_WARP 2   // fixed-point bilinear resample from the staged source box
+
+// gather-variant launch geometry (64 x 16 pixel blocks)
 #define MCS_TILE_W 64
 #define MCS_TILE_H 16
 
-#define MCS_TILE_BACKGROUND 0
-#define MCS_TILE_COPY 1
-#define MCS_TILE_WARP 2
-#define MCS_TILE_MIXED 3
+#define MCS_BOX_BYTES_MAX (40 * 1024)   // per staged source box
 
 struct mcs_plan {
     int n_layers;
@@ -69,7 +83,27 @@ struct mcs_plan {
     int device;
     McsLayer layers[MCS_MAX_LAYERS];
     int last_variant;
+    int force_variant;       // 0 = automatic, 1 = gather, 2 = tiled (diagnostics)
+    // tiled variant
+    int tiled_ok;            // tile table built and every box within limits
+    char tiled_why[160];     // why not, when tiled_ok == 0
+    int n_tiles;
+    int box_bytes;           // shared-memory bytes of one staging buffer (max over layers, 128-aligned)
+    McsTile* d_tiles;
+    McsLayer* d_layers;
+    // cache of the TMA descriptors of the last call (keyed by the source table)
+    unsigned char tmap_cache[MCS_MAX_LAYERS * 128 + 64];
+    const void* cache_src[MCS_MAX_LAYERS];
+    long long cache_pitch[MCS_MAX_LAYERS];
+    long long cache_fstride[MCS_MAX_LAYERS];
+    int cache_frames;
+    int cache_valid;
 };
 
 // 3x3 float64 inverse with cv::invert's association (host, no FMA contraction).
 bool mcs_invert3x3(const double* m, double* out);
+
+// Builds the tile table of the tiled variant (mcs_tiles.cu).  Never fails the plan: on any
+// problem it leaves tiled_ok = 0 with the reason in tiled_why and the gather variant is used.
+void mcs_plan_build_tiles(mcs_plan* plan);
+void mcs_plan_free_tiles(mcs_plan* plan);

@@ -125,14 +125,27 @@ extern "C" int mcs_plan_create(mcs_plan** out, int n_layers, int channels,
             L.affine = 1;
         }
     }
+    mcs_plan_build_tiles(p);   // never fails the plan: the gather variant covers what it cannot
     *out = p;
     return MCS_OK;
 }
 
 extern "C" int mcs_plan_destroy(mcs_plan* plan) {
     if (!plan) return MCS_OK;
+    mcs_plan_free_tiles(plan);
     delete plan;
     return MCS_OK;
 }
 
 extern "C" int mcs_plan_last_variant(const mcs_plan* plan) { return plan ? plan->last_variant : 0; }
+
+extern "C" int mcs_plan_force_variant(mcs_plan* plan, int variant) {
+    MCS_CHECK_ARG(plan != nullptr && variant >= 0 && variant <= 2, "mcs_plan_force_variant: bad argument");
+    plan->force_variant = variant;
+    return MCS_OK;
+}
+
+extern "C" const char* mcs_plan_tiled_status(const mcs_plan* plan) {
+    if (!plan) return "no plan";
+    return plan->tiled_ok ? "" : plan->tiled_why;
+}

@@ -1,0 +1,246 @@
+// Plan-time tiling for the tiled compositing kernel.
+//
+// The panorama is cut into work items ("tiles"), each owned by exactly one layer: layer k owns
+// rect_k minus rect_{k-1} (rectangles are nested, innermost first).  Tiles live on each layer's
+// own 128 x 16 cell grid, so a tile spans two whole 64-column coordinate blocks of OpenCV's
+// recipe.  A one-off kernel evaluates the exact fixed-point coordinates of every pixel of every
+// WARP tile and records the bounding box of the source pixels it touches; the host turns that
+// into the TMA box origin of the tile and the per-layer box size.
+#include "mcs_device.cuh"
+
+#include <vector>
+#include <string.h>
+
+struct TileBounds {
+    int min_sx, max_sx, min_sy, max_sy;
+    int touched;
+    int pad[3];
+};
+
+// One warp per tile.  sx / sy are clamped to [-2, src_w] / [-2, src_h]: at the clamp values both
+// taps of that axis are outside the source, so they read zero-filled box bytes, exactly what
+// BORDER_CONSTANT(0) returns.
+__global__ void __launch_bounds__(256)
+mcs_tile_bounds_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restrict__ layers, int n_tiles,
+                       TileBounds* __restrict__ out) {
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= n_tiles) return;
+    const McsTile tile = tiles[t];
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN, touched = 0;
+    if (tile.layer >= 0 && tile.cls == MCS_TILE_WARP) {
+        const McsLayer& L = layers[tile.layer];
+        const double m0 = L.mi[0], m3 = L.mi[3], m6 = L.mi[6];
+        const int w = tile.c1 - tile.c0;
+        const int n = w * tile.h;
+        for (int i = lane; i < n; i += 32) {
+            const int r = i / w, c = tile.c0 + (i - r * w);
+            const int xl = tile.cx0 + c - L.ox, yl = tile.y0 + r - L.oy;
+            const RowBlock rb = row_block(L.mi, xl & ~63, yl);
+            int X, Y;
+            fixed_coords(m0, m3, m6, rb, xl & 63, X, Y);
+            const int rsx = sat16(X >> 5), rsy = sat16(Y >> 5);
+            const bool in = ((unsigned)rsx < (unsigned)L.src_w || (unsigned)(rsx + 1) < (unsigned)L.src_w) &&
+                            ((unsigned)rsy < (unsigned)L.src_h || (unsigned)(rsy + 1) < (unsigned)L.src_h);
+            touched |= in ? 1 : 0;
+            const int sx = max(-2, min(L.src_w, rsx)), sy = max(-2, min(L.src_h, rsy));
+            mnx = min(mnx, sx); mxx = max(mxx, sx);
+            mny = min(mny, sy); mxy = max(mxy, sy);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, off));
+        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, off));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, off));
+        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, off));
+        touched |= __shfl_xor_sync(0xffffffffu, touched, off);
+    }
+    if (lane == 0) {
+        TileBounds b;
+        b.min_sx = mnx; b.max_sx = mxx; b.min_sy = mny; b.max_sy = mxy; b.touched = touched;
+        b.pad[0] = b.pad[1] = b.pad[2] = 0;
+        out[t] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Rect { int x0, y0, x1, y1; };
+
+inline bool empty(const Rect& r) { return r.x1 <= r.x0 || r.y1 <= r.y0; }
+
+inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// tiles of `piece` on the grid whose cell columns start at ox + 128*i
+void tile_piece(std::vector<McsTile>& out, const Rect& piece, int layer, int cls, int ox) {
+    if (empty(piece)) return;
+    const int i0 = floor_div(piece.x0 - ox, MCS_CELL_W), i1 = floor_div(piece.x1 - 1 - ox, MCS_CELL_W);
+    for (int y = piece.y0; y < piece.y1; y += MCS_CELL_H) {
+        for (int i = i0; i <= i1; ++i) {
+            McsTile t;
+            memset(&t, 0, sizeof(t));
+            t.cx0 = ox + i * MCS_CELL_W;
+            t.y0 = y;
+            t.c0 = (short)(std::max(piece.x0, t.cx0) - t.cx0);
+            t.c1 = (short)(std::min(piece.x1, t.cx0 + MCS_CELL_W) - t.cx0);
+            t.h = (short)std::min(MCS_CELL_H, piece.y1 - y);
+            t.layer = (short)layer;
+            t.cls = (short)cls;
+            out.push_back(t);
+        }
+    }
+}
+
+// outer minus inner (inner inside outer) as up to four rectangles
+void ring_pieces(const Rect& outer, const Rect& inner, Rect (&p)[4], int& n) {
+    n = 0;
+    if (empty(outer)) return;
+    if (empty(inner)) { p[n++] = outer; return; }
+    p[n++] = Rect{outer.x0, outer.y0, outer.x1, inner.y0};   // top band
+    p[n++] = Rect{outer.x0, inner.y1, outer.x1, outer.y1};   // bottom band
+    p[n++] = Rect{outer.x0, inner.y0, inner.x0, inner.y1};   // left strip
+    p[n++] = Rect{inner.x1, inner.y0, outer.x1, inner.y1};   // right strip
+}
+
+void why(mcs_plan* plan, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(plan->tiled_why, sizeof(plan->tiled_why), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace
+
+void mcs_plan_free_tiles(mcs_plan* plan) {
+    if (plan->d_tiles) cudaFree(plan->d_tiles);
+    if (plan->d_layers) cudaFree(plan->d_layers);
+    plan->d_tiles = nullptr;
+    plan->d_layers = nullptr;
+    plan->tiled_ok = 0;
+}
+
+void mcs_plan_build_tiles(mcs_plan* plan) {
+    plan->tiled_ok = 0;
+    plan->tiled_why[0] = 0;
+    const int C = plan->channels;
+    if (plan->out_w == 0 || plan->out_h == 0) { why(plan, "empty panorama"); return; }
+
+    // rectangles must be nested (innermost first) for the ring decomposition
+    Rect inner{0, 0, 0, 0};
+    for (int k = 0; k < plan->n_layers; ++k) {
+        const McsLayer& L = plan->layers[k];
+        Rect r{L.rx0, L.ry0, L.rx1, L.ry1};
+        if (!empty(inner) && (empty(r) || r.x0 > inner.x0 || r.y0 > inner.y0 || r.x1 < inner.x1 || r.y1 < inner.y1)) {
+            why(plan, "layer rectangles are not nested (layer %d)", k);
+            return;
+        }
+        if ((L.src_w * C) % 4 != 0) {
+            why(plan, "layer %d: source row of %d bytes is not a multiple of 4", k, L.src_w * C);
+            return;
+        }
+        if (!empty(r)) inner = r;
+    }
+
+    std::vector<McsTile> tiles;
+    inner = Rect{0, 0, 0, 0};
+    for (int k = 0; k < plan->n_layers; ++k) {
+        const McsLayer& L = plan->layers[k];
+        Rect r{L.rx0, L.ry0, L.rx1, L.ry1};
+        if (empty(r)) continue;
+        Rect pieces[4];
+        int n;
+        ring_pieces(r, inner, pieces, n);
+        for (int i = 0; i < n; ++i)
+            tile_piece(tiles, pieces[i], k, L.kind == MCS_LAYER_COPY ? MCS_TILE_COPY : MCS_TILE_WARP, L.ox);
+        inner = r;
+    }
+    {   // background: the panorama outside the outermost rectangle
+        Rect pieces[4];
+        int n;
+        ring_pieces(Rect{0, 0, plan->out_w, plan->out_h}, inner, pieces, n);
+        for (int i = 0; i < n; ++i) tile_piece(tiles, pieces[i], -1, MCS_TILE_ZERO, 0);
+    }
+    const int n_tiles = (int)tiles.size();
+    if (n_tiles == 0) { why(plan, "no tiles"); return; }
+
+    McsTile* d_tiles = nullptr;
+    McsLayer* d_layers = nullptr;
+    TileBounds* d_bounds = nullptr;
+    std::vector<TileBounds> bounds(n_tiles);
+    cudaError_t e = cudaMalloc(&d_tiles, sizeof(McsTile) * n_tiles);
+    if (e == cudaSuccess) e = cudaMalloc(&d_layers, sizeof(McsLayer) * MCS_MAX_LAYERS);
+    if (e == cudaSuccess) e = cudaMalloc(&d_bounds, sizeof(TileBounds) * n_tiles);
+    if (e == cudaSuccess) e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_layers, plan->layers, sizeof(McsLayer) * MCS_MAX_LAYERS, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        mcs_tile_bounds_kernel<<<(n_tiles + 7) / 8, 256>>>(d_tiles, d_layers, n_tiles, d_bounds);
+        mcs_count_launch(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(bounds.data(), d_bounds, sizeof(TileBounds) * n_tiles, cudaMemcpyDeviceToHost);
+    if (d_bounds) cudaFree(d_bounds);
+    if (e != cudaSuccess) {
+        why(plan, "tile analysis failed: %s", cudaGetErrorString(e));
+        if (d_tiles) cudaFree(d_tiles);
+        if (d_layers) cudaFree(d_layers);
+        return;
+    }
+
+    // classify, place the boxes, size them per layer
+    int bw4[MCS_MAX_LAYERS], bh[MCS_MAX_LAYERS];
+    for (int k = 0; k < MCS_MAX_LAYERS; ++k) bw4[k] = bh[k] = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+        McsTile& t = tiles[i];
+        if (t.layer < 0) continue;
+        const McsLayer& L = plan->layers[t.layer];
+        int need_w = 0, need_h = 0;
+        if (t.cls == MCS_TILE_COPY) {
+            const int first_byte = (t.cx0 + t.c0 - L.ox) * C, end_byte = (t.cx0 + t.c1 - L.ox) * C;
+            t.bx = floor_div(first_byte, 4);
+            t.by = t.y0 - L.oy;
+            need_w = (end_byte + 3) / 4 - t.bx + 1;   // +1: the realigning write-out reads one word ahead
+            need_h = t.h;
+        } else if (!bounds[i].touched) {
+            t.cls = MCS_TILE_ZERO;
+            continue;
+        } else {
+            const TileBounds& b = bounds[i];
+            t.bx = floor_div(b.min_sx * C, 4);
+            t.by = b.min_sy;
+            need_w = ((b.max_sx + 2) * C + 3) / 4 - t.bx + 1;   // taps sx, sx+1 and one spare word
+            need_h = b.max_sy + 2 - b.min_sy;
+        }
+        bw4[t.layer] = std::max(bw4[t.layer], need_w);
+        bh[t.layer] = std::max(bh[t.layer], need_h);
+    }
+    int box_bytes = 0;
+    for (int k = 0; k < plan->n_layers; ++k) {
+        if (bw4[k] == 0) { bw4[k] = 4; bh[k] = 1; }   // layer owns nothing that needs staging
+        bw4[k] = (bw4[k] + 3) & ~3;
+        if (bw4[k] > 256 || bh[k] > 256 || bw4[k] * 4 * bh[k] > MCS_BOX_BYTES_MAX) {
+            why(plan, "layer %d needs a %d x %d byte source box per tile (limit 1024 x 256, %d bytes)", k,
+                bw4[k] * 4, bh[k], MCS_BOX_BYTES_MAX);
+            cudaFree(d_tiles);
+            cudaFree(d_layers);
+            return;
+        }
+        plan->layers[k].bw4 = bw4[k];
+        plan->layers[k].bh = bh[k];
+        box_bytes = std::max(box_bytes, bw4[k] * 4 * bh[k]);
+    }
+    e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_layers, plan->layers, sizeof(McsLayer) * MCS_MAX_LAYERS, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        why(plan, "tile upload failed: %s", cudaGetErrorString(e));
+        cudaFree(d_tiles);
+        cudaFree(d_layers);
+        return;
+    }
+    plan->d_tiles = d_tiles;
+    plan->d_layers = d_layers;
+    plan->n_tiles = n_tiles;
+    plan->box_bytes = (box_bytes + 127) & ~127;
+    plan->tiled_ok = 1;
+}

@@ -142,6 +142,107 @@ def test_singular_homography_through_the_plan(cuda_device):
     assert np.array_equal(got, cv2.warpPerspective(a, M, (50, 30)))
 
 
+def _run_variant(st, labels, images, device, variant):
+    """Composite through a pinned kernel variant (1 = gather, 2 = tiled/TMA)."""
+    plan = st.plan([images[l].shape for l in labels], device)
+    if variant == 2:
+        assert plan.handle.tiled_status() == "", plan.handle.tiled_status()
+    plan.handle.force_variant(variant)
+    try:
+        dev = {l: torch.from_numpy(images[l]).to(device) for l in labels}
+        out = st.stitch(dev).cpu().numpy()
+        assert plan.handle.last_variant() == variant
+    finally:
+        plan.handle.force_variant(0)
+    return out
+
+
+@pytest.mark.parametrize("n,h,w,c,super_mode,off", [
+    (3, 720, 1280, 3, False, 0),
+    (3, 360, 640, 3, True, 0),
+    (4, 240, 320, 1, False, 7),
+    (4, 240, 320, 4, False, 3),
+    (6, 270, 480, 3, False, 0),
+    (8, 135, 240, 3, False, 5),
+    (2, 64, 48, 3, False, 0),
+])
+def test_tiled_variant_matches_cv2_and_gather(cuda_device, n, h, w, c, super_mode, off):
+    st, states, labels, images = synthetic_chain(n, h, w, c, super_mode=super_mode, kind="noise",
+                                                 xoffset=off, yoffset=off, use_points_first=True)
+    ref = stitcher_ref.stitch_chain(states, labels, images)
+    tiled = _run_variant(st, labels, images, cuda_device, 2)
+    gather = _run_variant(st, labels, images, cuda_device, 1)
+    _check(gather, ref)
+    _check(tiled, ref)
+
+
+@pytest.mark.parametrize("name,H", [
+    ("rot30", [[0.866, -0.5, 150.0], [0.5, 0.866, -20.0], [0, 0, 1]]),
+    ("rot90", [[0.0, -1.0, 400.0], [1.0, 0.0, 10.0], [0, 0, 1]]),
+    ("down", [[0.45, 0.02, 180.0], [0.01, 0.5, 30.0], [1e-5, 0, 1]]),
+    ("up", [[2.2, 0.1, 100.0], [-0.1, 2.4, 50.0], [1e-4, 2e-4, 1]]),
+    ("persp", [[1.0, 0.05, 120.0], [0.02, 1.1, 5.0], [6e-4, -2e-4, 1]]),
+    ("far_away", [[1.0, 0.0, 5000.0], [0.0, 1.0, 3000.0], [0, 0, 1]]),
+    ("flip", [[-1.0, 0.0, 500.0], [0.0, 1.0, 0.0], [0, 0, 1]]),
+])
+def test_tiled_variant_general_homographies(cuda_device, name, H):
+    from multicamera_stitching_b200 import Stitcher
+    rng = np.random.default_rng(11)
+    b = rng.integers(0, 256, (160, 256, 3), dtype=np.uint8)
+    a = rng.integers(0, 256, (192, 320, 3), dtype=np.uint8)
+    st = Stitcher({"A": b, "B": a})
+    st.stitchers[0].set_homography(np.array(H), a.shape, b.shape, 0, 0)
+    ost = stitcher_ref.new_state()
+    stitcher_ref.geometry_from_homography(ost, np.array(H), a.shape, b.shape, 0, 0)
+    ref = stitcher_ref.stitch_pair(ost, (b, a))
+    images = {"A": b, "B": a}
+    labels = ["A", "B"]
+    plan = st.plan([b.shape, a.shape], cuda_device)
+    if plan.handle.tiled_status() == "":
+        _check(_run_variant(st, labels, images, cuda_device, 2), ref)
+    _check(_run_variant(st, labels, images, cuda_device, 1), ref)
+    _check(st.stitch(images), ref)
+
+
+def test_tiled_variant_unaligned_destination(cuda_device):
+    st, states, labels, images = synthetic_chain(3, 144, 256, 3, kind="noise")
+    ref = stitcher_ref.stitch_chain(states, labels, images)
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    srcs = [torch.from_numpy(images[l]).to(cuda_device) for l in labels]
+    plan.handle.force_variant(2)
+    try:
+        for pad, shift in ((1, 0), (7, 3), (16, 5), (64, 1)):
+            row = plan.out_w * 3 + pad
+            buf = torch.full((plan.out_h * row + 64,), 0xAB, dtype=torch.uint8, device=cuda_device)
+            out = torch.as_strided(buf, (plan.out_h, plan.out_w, 3), (row, 3, 1), storage_offset=shift)
+            plan.run(srcs, out=out)
+            _check(out.cpu().numpy(), ref)
+            # padding bytes between rows stay untouched
+            flat = buf.cpu().numpy()
+            assert (flat[:shift] == 0xAB).all()
+            gap = flat[shift:shift + plan.out_h * row].reshape(plan.out_h, row)[:, plan.out_w * 3:]
+            assert (gap == 0xAB).all()
+    finally:
+        plan.handle.force_variant(0)
+
+
+def test_tiled_variant_batch(cuda_device):
+    st, states, labels, images = synthetic_chain(3, 144, 256, 3, kind="noise")
+    sets = []
+    for f in range(5):
+        _, _, _, im = synthetic_chain(3, 144, 256, 3, kind="noise", frame_index=f)
+        sets.append(im)
+    batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    plan.handle.force_variant(2)
+    try:
+        outb = st.stitch_batch(batch)
+    finally:
+        plan.handle.force_variant(0)
+    for f in range(5):
+        _check(outb[f].cpu().numpy(), stitcher_ref.stitch_chain(states, labels, sets[f]))
+
+
 def test_full_size_config2_vs_cv2(cuda_device):
     """BASELINE config 2 at full size (6 x 1080p): cv2 needs ~0.1 s."""
     st, states, labels, images = synthetic_chain(6, 1080, 1920, 3, kind="smooth")
