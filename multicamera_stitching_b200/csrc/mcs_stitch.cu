@@ -15,6 +15,7 @@
 #include "mcs_device.cuh"
 
 #include <string.h>
+#include <stdlib.h>
 
 struct LayerArgs {
     McsLayer g;
@@ -177,6 +178,7 @@ struct TiledArgs {
     int n_tiles;
     int n_frames;
     int box_bytes;                      // bytes of one staging buffer
+    int debug;                          // MCS_DEBUG_TILED: 1 = no TMA (all zero), 2 = TMA + wait only
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -299,6 +301,7 @@ mcs_stitch_tiled_kernel(const __grid_constant__ TiledArgs a) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
@@ -311,7 +314,7 @@ mcs_stitch_tiled_kernel(const __grid_constant__ TiledArgs a) {
         tma_load_3d(buf[slot], &a.tmap[tile.layer], tile.bx, tile.by, frame, &s_bar[slot]);
     };
     auto has_load = [&](long long item) -> bool {
-        return a.tiles[(int)(item % a.n_tiles)].cls != MCS_TILE_ZERO;
+        return a.debug != 1 && a.tiles[(int)(item % a.n_tiles)].cls != MCS_TILE_ZERO;
     };
 
     int loads_issued = 0;     // thread 0: loads issued so far
@@ -325,7 +328,7 @@ mcs_stitch_tiled_kernel(const __grid_constant__ TiledArgs a) {
     for (; item < n_items; item += gridDim.x) {
         const int t = (int)(item % a.n_tiles), frame = (int)(item / a.n_tiles);
         const McsTile tile = a.tiles[t];
-        const bool loaded = tile.cls != MCS_TILE_ZERO;
+        const bool loaded = a.debug != 1 && tile.cls != MCS_TILE_ZERO;
         const int slot = loads_used & 1;
 
         if (tile.cls == MCS_TILE_WARP && tid < 2 * MCS_CELL_H) {
@@ -354,6 +357,7 @@ mcs_stitch_tiled_kernel(const __grid_constant__ TiledArgs a) {
         }
         mbar_wait(&s_bar[slot], (uint32_t)((loads_used >> 1) & 1));
         loads_used += 1;
+        if (a.debug == 2) { write_rows(nullptr, 0, 0, g, a.dst_pitch, nbytes, tile.h, true); continue; }
         const McsLayer& L = a.layers[tile.layer];
         const int sp = L.bw4 * 4;
 
@@ -527,6 +531,7 @@ static int launch_tiled(mcs_plan* plan, const uint8_t* const* src, const int64_t
     a.n_tiles = plan->n_tiles;
     a.n_frames = n_frames;
     a.box_bytes = plan->box_bytes;
+    { const char* d = getenv("MCS_DEBUG_TILED"); a.debug = d ? atoi(d) : 0; }
 
     const size_t smem = tiled_smem_bytes(plan);
     void (*kern)(TiledArgs) = plan->channels == 1   ? mcs_stitch_tiled_kernel<1>

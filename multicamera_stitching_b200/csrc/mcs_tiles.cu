@@ -198,7 +198,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         int need_w = 0, need_h = 0;
         if (t.cls == MCS_TILE_COPY) {
             const int first_byte = (t.cx0 + t.c0 - L.ox) * C, end_byte = (t.cx0 + t.c1 - L.ox) * C;
-            t.bx = floor_div(first_byte, 4);
+            t.bx = 4 * floor_div(first_byte, 16);   // TMA: the box must start on a 16-byte boundary
             t.by = t.y0 - L.oy;
             need_w = (end_byte + 3) / 4 - t.bx + 1;   // +1: the realigning write-out reads one word ahead
             need_h = t.h;
@@ -207,7 +207,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             continue;
         } else {
             const TileBounds& b = bounds[i];
-            t.bx = floor_div(b.min_sx * C, 4);
+            t.bx = 4 * floor_div(b.min_sx * C, 16);   // TMA: the box must start on a 16-byte boundary
             t.by = b.min_sy;
             need_w = ((b.max_sx + 2) * C + 3) / 4 - t.bx + 1;   // taps sx, sx+1 and one spare word
             need_h = b.max_sy + 2 - b.min_sy;
