@@ -44,6 +44,9 @@ struct McsLayer {
     int affine;              // mi[6] == mi[7] == 0
     int bw4;                 // tiled variant: staged box width in 4-byte words (multiple of 4, <= 256)
     int bh;                  // tiled variant: staged box height in rows (<= 256)
+    int w_safe;              // |W| stays in [1e-3, 1e6] with one sign over the rectangle: the
+                             // branch-free division of the tiled kernel is exact there
+    int reserved;
 };
 
 // Work item of the tiled kernel: the part of one 128 x 16 cell of a layer's own canvas grid that
@@ -98,6 +101,8 @@ struct mcs_plan {
     long long cache_fstride[MCS_MAX_LAYERS];
     int cache_frames;
     int cache_valid;
+    int grid_ctas_per_sm;    // resident CTAs per SM of the tiled kernel (0 = not queried yet)
+    int n_sm;
 };
 
 // 3x3 float64 inverse with cv::invert's association (host, no FMA contraction).
@@ -107,3 +112,10 @@ bool mcs_invert3x3(const double* m, double* out);
 // problem it leaves tiled_ok = 0 with the reason in tiled_why and the gather variant is used.
 void mcs_plan_build_tiles(mcs_plan* plan);
 void mcs_plan_free_tiles(mcs_plan* plan);
+
+// Tiled variant (mcs_stitch_tiled.cu): why it cannot serve a call (nullptr = it can), and its launch.
+const char* mcs_tiled_blocker(const mcs_plan* plan, const uint8_t* const* src, const int64_t* pitch,
+                              const int64_t* fstride, int n_frames);
+int mcs_launch_tiled(mcs_plan* plan, const uint8_t* const* src, const int64_t* pitch, const int64_t* fstride,
+                     int n_frames, uint8_t* dst, int64_t dst_pitch, int64_t dst_frame_stride,
+                     cudaStream_t stream);

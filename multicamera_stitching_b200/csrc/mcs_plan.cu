@@ -120,6 +120,19 @@ extern "C" int mcs_plan_create(mcs_plan** out, int n_layers, int channels,
             }
             mcs_invert3x3(fwd_h + 9 * k, L.mi);  // singular -> all-zero inverse, as cv2 does
             L.affine = (L.mi[6] == 0.0 && L.mi[7] == 0.0) ? 1 : 0;
+            // W is affine in the pixel position, so its extremes over the rectangle sit at the corners
+            if (x1 > x0 && y1 > y0) {
+                double lo = 1e300, hi = -1e300;
+                for (int cx = 0; cx < 2; ++cx)
+                    for (int cy = 0; cy < 2; ++cy) {
+                        const double xl = (cx ? x1 - 1 : x0) - L.ox, yl = (cy ? y1 - 1 : y0) - L.oy;
+                        const double W = L.mi[6] * xl + L.mi[7] * yl + L.mi[8];
+                        lo = W < lo ? W : lo;
+                        hi = W > hi ? W : hi;
+                    }
+                const bool pos = lo >= 1e-3 && hi <= 1e6, neg = hi <= -1e-3 && lo >= -1e6;
+                L.w_safe = (pos || neg) ? 1 : 0;
+            }
         } else {
             L.mi[0] = L.mi[4] = L.mi[8] = 1.0;
             L.affine = 1;
