@@ -59,10 +59,10 @@ struct McsTile {
     short h;         // rows, 1..16
     short layer;     // owner layer, -1 for background
     short cls;       // MCS_TILE_*
-    short flags;
+    short flags;     // bit 0: tap coordinates need clamping
     int bx;          // staged box origin: 4-byte word index within the source row (may be negative)
     int by;          // staged box origin: source row (may be negative)
-    int reserved;
+    int reserved;    // bytes of the staged box (mbarrier transaction count)
 };
 static_assert(sizeof(McsTile) == 32, "McsTile must stay 32 bytes");
 

@@ -14,7 +14,8 @@
 struct TileBounds {
     int min_sx, max_sx, min_sy, max_sy;
     int touched;
-    int pad[3];
+    int clamped;   // some tap coordinate had to be clamped (lies 2+ pixels outside the source)
+    int pad[2];
 };
 
 // One warp per tile.  sx / sy are clamped to [-2, src_w] / [-2, src_h]: at the clamp values both
@@ -27,7 +28,7 @@ mcs_tile_bounds_kernel(const McsTile* __restrict__ tiles, const McsLayer* __rest
     const int lane = threadIdx.x & 31;
     if (t >= n_tiles) return;
     const McsTile tile = tiles[t];
-    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN, touched = 0;
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN, touched = 0, clamped = 0;
     if (tile.layer >= 0 && tile.cls == MCS_TILE_WARP) {
         const McsLayer& L = layers[tile.layer];
         const double m0 = L.mi[0], m3 = L.mi[3], m6 = L.mi[6];
@@ -44,6 +45,7 @@ mcs_tile_bounds_kernel(const McsTile* __restrict__ tiles, const McsLayer* __rest
                             ((unsigned)rsy < (unsigned)L.src_h || (unsigned)(rsy + 1) < (unsigned)L.src_h);
             touched |= in ? 1 : 0;
             const int sx = max(-2, min(L.src_w, rsx)), sy = max(-2, min(L.src_h, rsy));
+            clamped |= (sx != (X >> 5) || sy != (Y >> 5)) ? 1 : 0;
             mnx = min(mnx, sx); mxx = max(mxx, sx);
             mny = min(mny, sy); mxy = max(mxy, sy);
         }
@@ -55,11 +57,13 @@ mcs_tile_bounds_kernel(const McsTile* __restrict__ tiles, const McsLayer* __rest
         mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, off));
         mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, off));
         touched |= __shfl_xor_sync(0xffffffffu, touched, off);
+        clamped |= __shfl_xor_sync(0xffffffffu, clamped, off);
     }
     if (lane == 0) {
         TileBounds b;
         b.min_sx = mnx; b.max_sx = mxx; b.min_sy = mny; b.max_sy = mxy; b.touched = touched;
-        b.pad[0] = b.pad[1] = b.pad[2] = 0;
+        b.clamped = clamped;
+        b.pad[0] = b.pad[1] = 0;
         out[t] = b;
     }
 }
@@ -209,6 +213,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             const TileBounds& b = bounds[i];
             t.bx = 4 * floor_div(b.min_sx * C, 16);   // TMA: the box must start on a 16-byte boundary
             t.by = b.min_sy;
+            t.flags = (short)(b.clamped ? 1 : 0);
             need_w = ((b.max_sx + 2) * C + 3) / 4 - t.bx + 1;   // taps sx, sx+1 and one spare word
             need_h = b.max_sy + 2 - b.min_sy;
         }
@@ -230,6 +235,8 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         plan->layers[k].bh = bh[k];
         box_bytes = std::max(box_bytes, bw4[k] * 4 * bh[k]);
     }
+    for (int i = 0; i < n_tiles; ++i)   // bytes the TMA delivers for the tile (mbarrier transaction count)
+        if (tiles[i].layer >= 0) tiles[i].reserved = bw4[tiles[i].layer] * 4 * bh[tiles[i].layer];
     e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_layers, plan->layers, sizeof(McsLayer) * MCS_MAX_LAYERS, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
