@@ -270,6 +270,14 @@ def run_ours(args, rank, local_rank, world):
     peak, peak_src = measured_peak()
 
     # ---- end to end through the host-facing sequence API -------------------------
+    if args.no_e2e:   # kernel experiments only: the line then carries no end-to-end number
+        if world > 1:
+            dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps({"metric": "panoramas_per_sec", "value": pps, "ms_per_step": ms_step,
+                              "roofline": {"achieved": achieved, "frac": achieved / peak}, "parity": parity,
+                              "gpu_launches": launches, "clocks": clocks, "e2e": None}), flush=True)
+        return
     pipe = SequencePipeline(st, shapes, device, chunk=args.chunk, depth=3)
     host_frames = {l: pinned_like((e2e_batch,) + tuple(images[l].shape)) for l in labels}
     for l in labels:
@@ -352,6 +360,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=4, help="frame-sets per pipeline chunk of the e2e path")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel experiments: skip the end-to-end leg")
     ap.add_argument("--ref-panos-per-step", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libmcs_b200.so")
+# $MCS_B200_LIB points the binding at another build of the same library (kernel experiments)
+LIB_PATH = os.environ.get("MCS_B200_LIB") or os.path.join(_PKG_DIR, "libmcs_b200.so")
 
 MCS_OK = 0
 MCS_MAX_LAYERS = 16

@@ -223,7 +223,9 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
     int box_bytes = 0;
     for (int k = 0; k < plan->n_layers; ++k) {
         if (bw4[k] == 0) { bw4[k] = 4; bh[k] = 1; }   // layer owns nothing that needs staging
-        bw4[k] = (bw4[k] + 3) & ~3;
+        // box pitch a multiple of 128 bytes (32 banks): when the lanes of a warp straddle two
+        // source rows their words still fall into disjoint shared-memory banks
+        bw4[k] = (bw4[k] + 31) & ~31;
         if (bw4[k] > 256 || bh[k] > 256 || bw4[k] * 4 * bh[k] > MCS_BOX_BYTES_MAX) {
             why(plan, "layer %d needs a %d x %d byte source box per tile (limit 1024 x 256, %d bytes)", k,
                 bw4[k] * 4, bh[k], MCS_BOX_BYTES_MAX);
