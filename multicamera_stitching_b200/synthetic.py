@@ -79,3 +79,50 @@ def homography_from_points(height, width, canvas_width, overlap=0.4):
            (x0 + 0.985 * width - 4.0, 0.98 * height + 9.0), (x0 - 2.0, 0.99 * height + 14.0)]
     M, _ = CalculateProjectionMatrix(src, dst)
     return M
+
+
+# ---------------------------------------------------------------------------
+# recalibration workload (BASELINE.json config 4): feature-rich image pairs
+def make_textured(height, width, seed=0, channels=3):
+    """A frame full of corners (random filled rectangles and discs, lightly
+    blurred): ``cv2.ORB_create(2000)`` finds its full quota of key-points on it,
+    which the smooth frames above do not offer."""
+    rng = np.random.default_rng(10_000 + int(seed))
+    img = np.full((height, width, 3), 96, np.uint8)
+    n_shapes = max(50, height * width // 1400)
+    for i in range(n_shapes):
+        x, y = int(rng.integers(0, width)), int(rng.integers(0, height))
+        r = int(rng.integers(4, 40))
+        colour = tuple(int(v) for v in rng.integers(0, 255, 3))
+        if i % 2:
+            cv2.circle(img, (x, y), r, colour, -1)
+        else:
+            cv2.rectangle(img, (x, y), (x + r, y + int(rng.integers(4, 40))), colour, -1)
+    img = cv2.GaussianBlur(img, (0, 0), 1.0)
+    if channels == 1:
+        return np.ascontiguousarray(img[:, :, 0])
+    return np.ascontiguousarray(img)
+
+
+def make_pair(height, width, seed=0, overlap=0.6, noise_sigma=2.0):
+    """``(imageB, imageA, H_true)``: two views of one textured scene.  ``H_true``
+    maps imageA pixel coordinates into imageB's frame (the homography
+    ``StitcherBase.calibrate`` has to recover): imageA is the scene resampled
+    through ``inv(H_true)`` plus sensor noise, imageB a crop of the scene."""
+    scene_w = int(width * (2.0 - overlap)) + 64
+    scene = make_textured(height + 64, scene_w, seed)
+    rng = np.random.default_rng(20_000 + int(seed))
+    imageB = scene[32:32 + height, 32:32 + width].copy()
+    tx = (1.0 - overlap) * width
+    H_true = np.array([[0.97, 0.015, tx + 1.3],
+                       [-0.01, 0.985, 6.7],
+                       [1.5e-5 * (720.0 / height), -0.8e-5 * (720.0 / height), 1.0]], dtype=np.float64)
+    # scene coordinates = imageB coordinates + 32
+    T = np.array([[1, 0, 32.0], [0, 1, 32.0], [0, 0, 1]], dtype=np.float64)
+    A_to_scene = T @ H_true
+    imageA = cv2.warpPerspective(scene, np.linalg.inv(A_to_scene), (width, height), flags=cv2.INTER_LINEAR)
+    for im in (imageA, imageB):
+        noise = rng.normal(0.0, noise_sigma, im.shape)
+        np.clip(im.astype(np.float64) + noise, 0, 255, out=noise)
+        im[...] = noise.astype(np.uint8)
+    return np.ascontiguousarray(imageB), np.ascontiguousarray(imageA), H_true
