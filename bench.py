@@ -188,29 +188,18 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch
-    import torch.distributed as dist
     from multicamera_stitching_b200 import _cabi
     from multicamera_stitching_b200.sequence import SequencePipeline, pinned_like
+    from multicamera_stitching_b200.shard import ShardContext
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the GPU arm)")
     _cabi.load()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    ctx = ShardContext.from_env(backend="nccl", device=device)   # control path only: barrier + max time
+    barrier = ctx.barrier
+    max_over_ranks = ctx.max_over_ranks
 
     n_cams, H, W, batch, e2e_batch = WORKLOADS[args.workload]
     if args.batch:
@@ -271,8 +260,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- end to end through the host-facing sequence API -------------------------
     if args.no_e2e:   # kernel experiments only: the line then carries no end-to-end number
-        if world > 1:
-            dist.destroy_process_group()
+        ctx.close()
         if rank == 0:
             print(json.dumps({"metric": "panoramas_per_sec", "value": pps, "ms_per_step": ms_step,
                               "roofline": {"achieved": achieved, "frac": achieved / peak}, "parity": parity,
@@ -313,8 +301,7 @@ def run_ours(args, rank, local_rank, world):
                          "(oracle/stitcher_ref.py, StitcherClass.py:131-136), %d threads"
                          % (n, args.workload, dt, cv2.__version__, threads)}
 
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
     if rank != 0:
         return
     line = {

@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""Generates the fixtures under tests/golden/ (run in the authoring container, where
+/root/reference and cv2 are present; the fixtures travel, this script's inputs do not).
+
+  python scripts/make_golden.py [/root/reference]
+
+  utils_reference.npz   outputs of the REFERENCE'S OWN PostScripts/Calibration_Utils/Utils.py
+                        (imported from the reference tree, it runs under Python 3):
+                        get_projection_point_dst / _src, CalculateProjectionMatrix
+  warp_cv2.npz          cv2.warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0) called as
+                        StitcherClass.py:239 calls it, on a seeded noise image
+  chain_cv2.npz         the 3-camera warp+paste chain of StitcherClass.py:131-136 / :239-241
+                        (oracle/stitcher_ref.py driving cv2), with its geometry (:293-351)
+  match_cv2.npz         cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) + the ratio loop of :428-433
+                        on seeded descriptors with planted partners and exact ties
+All inputs are regenerated from seeds by the tests; only the expected outputs (and the
+descriptor sets) are stored.
+"""
+import importlib.util
+import os
+import sys
+
+import cv2
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def load_reference_utils(ref_root):
+    path = os.path.join(ref_root, "PostScripts", "Calibration_Utils", "Utils.py")
+    spec = importlib.util.spec_from_file_location("reference_Utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def utils_cases():
+    rng = np.random.default_rng(42)
+    quads = []
+    for _ in range(12):
+        w, h = int(rng.integers(200, 2000)), int(rng.integers(200, 1200))
+        src = np.float64([[0, 0], [w, 0], [w, h], [0, h]]) + rng.uniform(-30, 30, (4, 2))
+        dst = src * rng.uniform(0.6, 1.4) + rng.uniform(-120, 400, (1, 2)) + rng.uniform(-25, 25, (4, 2))
+        quads.append((src, dst))
+    pts = np.concatenate([rng.uniform(-50, 2100, (40, 2)), np.ones((40, 1))], axis=1)
+    return quads, pts
+
+
+def golden_utils(ref_root):
+    U = load_reference_utils(ref_root)
+    quads, pts = utils_cases()
+    Ms, INVMs, fwd, back = [], [], [], []
+    for src, dst in quads:
+        M, INVM = U.CalculateProjectionMatrix(src, dst)
+        Ms.append(M)
+        INVMs.append(INVM)
+        fwd.append([U.get_projection_point_dst(tuple(p), M) for p in pts])
+        back.append([U.get_projection_point_src(tuple(p), INVM) for p in pts])
+    np.savez_compressed(os.path.join(OUT, "utils_reference.npz"),
+                        src=np.array([q[0] for q in quads]), dst=np.array([q[1] for q in quads]), pts=pts,
+                        M=np.array(Ms), INVM=np.array(INVMs), fwd=np.array(fwd, dtype=np.int64),
+                        back=np.array(back, dtype=np.int64))
+
+
+WARP_HOMS = {
+    "near_identity": [[0.98, 0.015, 13.2], [-0.01, 1.003, 4.7], [1.1e-5, -4e-6, 1.0]],
+    "rotate_scale": [[0.61, -0.52, 60.0], [0.48, 0.66, -5.0], [2e-4, 1e-4, 1.0]],
+    "strong_perspective": [[1.2, 0.1, -20.0], [0.05, 1.3, -10.0], [1.5e-3, 8e-4, 1.0]],
+}
+
+
+def warp_source():
+    return np.random.default_rng(1234).integers(0, 256, size=(61, 83, 3), dtype=np.uint8)
+
+
+def golden_warp():
+    src = warp_source()
+    out = {}
+    for name, H in WARP_HOMS.items():
+        out[name] = cv2.warpPerspective(src, np.array(H, dtype=np.float64), (140, 90))
+    np.savez_compressed(os.path.join(OUT, "warp_cv2.npz"), **out)
+
+
+def golden_chain():
+    from helpers import synthetic_chain
+    from oracle import stitcher_ref
+    st, states, labels, images = synthetic_chain(3, 96, 128, 3, kind="noise", xoffset=3, yoffset=5)
+    pano = stitcher_ref.stitch_chain(states, labels, images)
+    geo = {}
+    for k, s in enumerate(states):
+        geo["cachedAH_%d" % k] = np.asarray(s["cachedAH"], dtype=np.float64)
+        geo["Bpts_%d" % k] = np.asarray(s["Bpts"], dtype=np.int64)
+        geo["ABSize_%d" % k] = np.asarray(s["ABSize"], dtype=np.int64)
+        geo["limits_%d" % k] = np.asarray([s["x_limits"], s["y_limits"]], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "chain_cv2.npz"), pano=pano, **geo)
+
+
+def match_descriptors():
+    rng = np.random.default_rng(77)
+    fb = rng.integers(0, 256, size=(350, 32), dtype=np.uint8)
+    fa = rng.integers(0, 256, size=(300, 32), dtype=np.uint8)
+    fa[:150] = fb[rng.permutation(350)[:150]]
+    fa[:150, :3] ^= rng.integers(0, 256, size=(150, 3), dtype=np.uint8) & 0x21
+    fb[340] = fb[7]      # exact ties
+    fb[341] = fb[7]
+    fa[299] = fb[7]
+    return fa, fb
+
+
+def golden_match():
+    fa, fb = match_descriptors()
+    raw = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(fa, fb, 2)
+    idx = np.array([[m[0].trainIdx, m[1].trainIdx] for m in raw], dtype=np.int32)
+    dist = np.array([[int(m[0].distance), int(m[1].distance)] for m in raw], dtype=np.int32)
+    matches = np.array([(m[0].trainIdx, m[0].queryIdx) for m in raw
+                        if len(m) == 2 and m[0].distance < m[1].distance * 0.75], dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, "match_cv2.npz"), fa=fa, fb=fb, idx=idx, dist=dist, matches=matches)
+
+
+if __name__ == "__main__":
+    ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    os.makedirs(OUT, exist_ok=True)
+    golden_utils(ref_root)
+    golden_warp()
+    golden_chain()
+    golden_match()
+    with open(os.path.join(OUT, "README.md"), "w") as f:
+        f.write("Fixtures written by scripts/make_golden.py (cv2 %s, numpy %s).\n"
+                "utils_reference.npz comes from the reference's own Calibration_Utils/Utils.py;\n"
+                "the others from cv2 driven as PostScripts/Stitcher/StitcherClass.py drives it.\n"
+                % (cv2.__version__, np.__version__))
+    for n in sorted(os.listdir(OUT)):
+        print(n, os.path.getsize(os.path.join(OUT, n)))

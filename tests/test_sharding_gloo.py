@@ -1,0 +1,96 @@
+"""CPU, world_size 2, gloo: the multi-GPU host logic of the sequence path (frame-range
+sharding, barrier, max-over-ranks timing, per-frame summaries gathered to rank 0).  The data
+path itself has no collective, so each rank stands in for its GPU with the cv2 oracle chain on
+a tiny configuration and the test checks that the sharded job reproduces the unsharded one."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from multicamera_stitching_b200.sequence import shard_range
+
+
+def test_shard_ranges_tile_the_sequence():
+    for n in (0, 1, 7, 10, 16, 10000):
+        for world in (1, 2, 3, 4, 8):
+            ranges = [shard_range(n, world, r) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [hi - lo for lo, hi in ranges]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _checksum(img):
+    return int(np.asarray(img, dtype=np.uint64).sum() % (2 ** 62))
+
+
+def _worker(rank, world, port, n_frames, tmpdir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(here))
+    from helpers import synthetic_chain
+    from multicamera_stitching_b200 import synthetic
+    from multicamera_stitching_b200.shard import ShardContext
+    from oracle import stitcher_ref
+
+    ctx = ShardContext.from_env(backend="gloo", device="cpu")
+    assert ctx.world_size == world and ctx.rank == rank
+    st, states, labels, _ = synthetic_chain(3, 48, 64, 3, kind="smooth")
+    lo, hi = ctx.frame_range(n_frames)
+    ctx.barrier()
+    sums = []
+    for f in range(lo, hi):
+        frames = synthetic.make_frames(3, 48, 64, 3, frame_index=f, kind="smooth")
+        sums.append(_checksum(stitcher_ref.stitch_chain(states, labels, frames)))
+    ctx.barrier()
+    elapsed = ctx.max_over_ranks(10.0 + rank)          # stands in for a per-rank device time
+    total = ctx.sum_over_ranks(hi - lo)
+    gathered = ctx.gather_frame_summaries(lo, sums)
+    if rank == 0:
+        torch.save({"elapsed": elapsed, "total": total, "gathered": gathered}, os.path.join(tmpdir, "rank0.pt"))
+    else:
+        assert gathered is None
+    ctx.close()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_sequence_equals_unsharded(tmp_path):
+    n_frames, world = 7, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_frames, str(tmp_path)), nprocs=world, join=True)
+    res = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
+    assert res["elapsed"] == 11.0                      # max over ranks
+    assert res["total"] == n_frames                    # every frame processed exactly once
+    # unsharded reference, frame by frame
+    from helpers import synthetic_chain
+    from multicamera_stitching_b200 import synthetic
+    from oracle import stitcher_ref
+    st, states, labels, _ = synthetic_chain(3, 48, 64, 3, kind="smooth")
+    want = [_checksum(stitcher_ref.stitch_chain(states, labels,
+                                                synthetic.make_frames(3, 48, 64, 3, frame_index=f, kind="smooth")))
+            for f in range(n_frames)]
+    assert res["gathered"].tolist() == want
+
+
+def test_single_rank_context_needs_no_process_group():
+    from multicamera_stitching_b200.shard import ShardContext
+    ctx = ShardContext(0, 1, None)
+    assert ctx.frame_range(10) == (0, 10)
+    ctx.barrier()
+    assert ctx.max_over_ranks(3.5) == 3.5 and ctx.sum_over_ranks(2) == 2.0
+    assert ctx.gather_frame_summaries(0, [1, 2, 3]).tolist() == [1, 2, 3]
