@@ -90,13 +90,14 @@ __global__ void __launch_bounds__(256)
 mcs_stitch_gather_kernel(const __grid_constant__ StitchArgs a, unsigned long long* __restrict__ owned) {
     const int x_first = blockIdx.x * MCS_TILE_W + threadIdx.x * 4;
     const int y = blockIdx.y * MCS_TILE_H + threadIdx.y;
-    if (y >= a.out_h || x_first >= a.out_w) return;
+    const bool inside = y < a.out_h && x_first < a.out_w;
+    if (!STATS && !inside) return;   // the counter keeps whole warps alive for its warp-level merge
     const int frame = blockIdx.z;
 
     int prev_owner = -2, prev_xb = 0;
     RowBlock rb = {0.0, 0.0, 0.0};
     uint8_t px[4 * C];
-    const int n_px = min(4, a.out_w - x_first);
+    const int n_px = inside ? min(4, a.out_w - x_first) : 0;
 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -104,6 +105,7 @@ mcs_stitch_gather_kernel(const __grid_constant__ StitchArgs a, unsigned long lon
 #pragma unroll
         for (int c = 0; c < C; ++c) v[c] = 0;
         const int x = x_first + i;
+        int counted = -1;   // STATS: layer this pixel is counted for
         if (i < n_px) {
             const int k = find_owner(a, x, y);
             if (k >= 0) {
@@ -130,8 +132,13 @@ mcs_stitch_gather_kernel(const __grid_constant__ StitchArgs a, unsigned long lon
                         sample_u8<C>(src, L.pitch, L.g.src_w, L.g.src_h, X, Y, v);
                     }
                 }
-                if (STATS && touched) atomicAdd(owned + k, 1ULL);
+                if (STATS && touched) counted = k;
             }
+        }
+        if (STATS) {   // one atomic per (warp, layer) instead of one per pixel
+            const unsigned peers = __match_any_sync(0xffffffffu, counted);
+            if (counted >= 0 && (threadIdx.y * blockDim.x + threadIdx.x) % 32 == __ffs(peers) - 1)
+                atomicAdd(owned + counted, (unsigned long long)__popc(peers));
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) px[i * C + c] = (uint8_t)v[c];
