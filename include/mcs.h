@@ -128,6 +128,10 @@ int mcs_plan_force_variant(mcs_plan* plan, int variant);
  * not (the gather variant then serves every call). */
 const char* mcs_plan_tiled_status(const mcs_plan* plan);
 
+/* Resident CTAs per SM of the tiled kernel as launched for this plan (0 before its first
+ * tiled launch); the persistent grid is this times the SM count.  Diagnostics. */
+int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan);
+
 /* Number of kernels this library has launched in the calling process. */
 int64_t mcs_launch_count(void);
 

@@ -22,7 +22,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_destroy",
     "mcs_plan_owned_pixels", "mcs_stitch_u8", "mcs_plan_last_variant", "mcs_plan_force_variant",
-    "mcs_plan_tiled_status", "mcs_launch_count",
+    "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_launch_count",
     "mcs_match_hamming_top2", "mcs_ransac_homography",
 )
 
@@ -74,6 +74,8 @@ def load(build_if_missing=False):
     lib.mcs_plan_last_variant.argtypes = [_vp]
     lib.mcs_plan_force_variant.restype = ctypes.c_int
     lib.mcs_plan_force_variant.argtypes = [_vp, ctypes.c_int]
+    lib.mcs_plan_tiled_ctas_per_sm.restype = ctypes.c_int
+    lib.mcs_plan_tiled_ctas_per_sm.argtypes = [_vp]
     lib.mcs_plan_tiled_status.restype = ctypes.c_char_p
     lib.mcs_plan_tiled_status.argtypes = [_vp]
     lib.mcs_launch_count.restype = ctypes.c_int64
@@ -162,6 +164,9 @@ class Plan(object):
     def force_variant(self, variant):
         """0 = automatic, 1 = gather kernel, 2 = tiled (TMA-staged) kernel."""
         check(_lib.mcs_plan_force_variant(self._h, int(variant)), "mcs_plan_force_variant")
+
+    def tiled_ctas_per_sm(self):
+        return int(_lib.mcs_plan_tiled_ctas_per_sm(self._h))
 
     def tiled_status(self):
         """'' when the tiled variant is available, else why it is not."""

@@ -59,7 +59,7 @@ struct McsTile {
     short h;         // rows, 1..16
     short layer;     // owner layer, -1 for background
     short cls;       // MCS_TILE_*
-    short flags;     // bit 0: tap coordinates need clamping
+    short flags;     // estimated cost of one frame of the tile (work-split weight)
     int bx;          // staged box origin: 4-byte word index within the source row (may be negative)
     int by;          // staged box origin: source row (may be negative)
     int reserved;    // bytes of the staged box (mbarrier transaction count)
@@ -78,6 +78,9 @@ static_assert(sizeof(McsTile) == 32, "McsTile must stay 32 bytes");
 #define MCS_TILE_H 16
 
 #define MCS_BOX_BYTES_MAX (40 * 1024)   // per staged source box
+
+#define MCS_SCHED_SLOTS 4
+#define MCS_SCHED_MAX_GRID 2047
 
 struct mcs_plan {
     int n_layers;
@@ -103,7 +106,17 @@ struct mcs_plan {
     int cache_valid;
     int grid_ctas_per_sm;    // resident CTAs per SM of the tiled kernel (0 = not queried yet)
     int n_sm;
+    // Work split of the tiled kernel.  The (tile, frame) units, ordered tile-major, are cut into
+    // one contiguous range of equal estimated cost per CTA; h_cum[t] = summed per-frame cost of
+    // tiles 0..t-1.  The cut positions depend on (n_frames, grid) and are cached in a few slots.
+    long long* h_cum;        // host, n_tiles + 1 entries
+    int class_first[4];      // the tile table is sorted WARP, COPY, ZERO: first tile of each class, then n_tiles
+    int2* d_sched;           // device, MCS_SCHED_SLOTS x 3 x (MCS_SCHED_MAX_GRID + 1) entries {tile, frame}
+    int sched_frames[MCS_SCHED_SLOTS];
+    int sched_grid[MCS_SCHED_SLOTS];
+    int sched_next;          // slot overwritten next
 };
+
 
 // 3x3 float64 inverse with cv::invert's association (host, no FMA contraction).
 bool mcs_invert3x3(const double* m, double* out);
@@ -115,7 +128,7 @@ void mcs_plan_free_tiles(mcs_plan* plan);
 
 // Tiled variant (mcs_stitch_tiled.cu): why it cannot serve a call (nullptr = it can), and its launch.
 const char* mcs_tiled_blocker(const mcs_plan* plan, const uint8_t* const* src, const int64_t* pitch,
-                              const int64_t* fstride, int n_frames);
+                              const int64_t* fstride, int n_frames, int64_t dst_pitch);
 int mcs_launch_tiled(mcs_plan* plan, const uint8_t* const* src, const int64_t* pitch, const int64_t* fstride,
                      int n_frames, uint8_t* dst, int64_t dst_pitch, int64_t dst_frame_stride,
                      cudaStream_t stream);

@@ -162,3 +162,5 @@ extern "C" const char* mcs_plan_tiled_status(const mcs_plan* plan) {
     if (!plan) return "no plan";
     return plan->tiled_ok ? "" : plan->tiled_why;
 }
+
+extern "C" int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan) { return plan ? plan->grid_ctas_per_sm : 0; }

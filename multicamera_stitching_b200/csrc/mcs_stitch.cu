@@ -215,7 +215,7 @@ extern "C" int mcs_stitch_u8(const mcs_plan* plan_c, const uint8_t* const* src,
     }
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const int force = plan->force_variant;
-    const char* blocker = mcs_tiled_blocker(plan, src, src_pitch_bytes, src_frame_stride, n_frames);
+    const char* blocker = mcs_tiled_blocker(plan, src, src_pitch_bytes, src_frame_stride, n_frames, dst_pitch_bytes);
     if (force == 2 && blocker) {
         mcs_set_error("mcs_stitch_u8: tiled variant forced but unavailable: %s", blocker);
         return MCS_ERR_UNSUPPORTED;

@@ -8,7 +8,9 @@
 // into the TMA box origin of the tile and the per-layer box size.
 #include "mcs_device.cuh"
 
+#include <algorithm>
 #include <vector>
+#include <stdlib.h>
 #include <string.h>
 
 struct TileBounds {
@@ -77,7 +79,8 @@ inline bool empty(const Rect& r) { return r.x1 <= r.x0 || r.y1 <= r.y0; }
 
 inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-// tiles of `piece` on the grid whose cell columns start at ox + 128*i
+// tiles of `piece` on the grid whose cell columns start at ox + 128*i (the kernel takes any ox;
+// the plan anchors every layer at panorama column 0, see mcs_plan_build_tiles)
 void tile_piece(std::vector<McsTile>& out, const Rect& piece, int layer, int cls, int ox) {
     if (empty(piece)) return;
     const int i0 = floor_div(piece.x0 - ox, MCS_CELL_W), i1 = floor_div(piece.x1 - 1 - ox, MCS_CELL_W);
@@ -120,9 +123,25 @@ void why(mcs_plan* plan, const char* fmt, ...) {
 void mcs_plan_free_tiles(mcs_plan* plan) {
     if (plan->d_tiles) cudaFree(plan->d_tiles);
     if (plan->d_layers) cudaFree(plan->d_layers);
+    if (plan->d_sched) cudaFree(plan->d_sched);
+    free(plan->h_cum);
     plan->d_tiles = nullptr;
     plan->d_layers = nullptr;
+    plan->d_sched = nullptr;
+    plan->h_cum = nullptr;
     plan->tiled_ok = 0;
+}
+
+// Estimated cost of one frame of a tile, in consumer-warp instructions of the tiled kernel: the
+// slowest warp sets the pace of a cell (all warps share the staged box).
+static int tile_cost(const McsTile& t) {
+    if (t.cls == MCS_TILE_ZERO) return 40;
+    if (t.cls == MCS_TILE_COPY) return 90;
+    int groups = 0;
+    for (int g = 0; g < 4; ++g)
+        if (32 * g < t.c1 && 32 * g + 32 > t.c0) ++groups;
+    const int px = groups * (t.h > 8 ? 2 : 1);     // pixels per thread of the busiest warp
+    return 63 + 26 * px;
 }
 
 void mcs_plan_build_tiles(mcs_plan* plan) {
@@ -157,7 +176,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         int n;
         ring_pieces(r, inner, pieces, n);
         for (int i = 0; i < n; ++i)
-            tile_piece(tiles, pieces[i], k, L.kind == MCS_LAYER_COPY ? MCS_TILE_COPY : MCS_TILE_WARP, L.ox);
+            tile_piece(tiles, pieces[i], k, L.kind == MCS_LAYER_COPY ? MCS_TILE_COPY : MCS_TILE_WARP, 0);
         inner = r;
     }
     {   // background: the panorama outside the outermost rectangle
@@ -213,7 +232,6 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             const TileBounds& b = bounds[i];
             t.bx = 4 * floor_div(b.min_sx * C, 16);   // TMA: the box must start on a 16-byte boundary
             t.by = b.min_sy;
-            t.flags = (short)(b.clamped ? 1 : 0);
             need_w = ((b.max_sx + 2) * C + 3) / 4 - t.bx + 1;   // taps sx, sx+1 and one spare word
             need_h = b.max_sy + 2 - b.min_sy;
         }
@@ -239,14 +257,43 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
     }
     for (int i = 0; i < n_tiles; ++i)   // bytes the TMA delivers for the tile (mbarrier transaction count)
         if (tiles[i].layer >= 0) tiles[i].reserved = bw4[tiles[i].layer] * 4 * bh[tiles[i].layer];
-    e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
+    // Work split: tiles grouped by class (each class keeps its layer / row / column order, so a
+    // CTA's range covers neighbouring cells), costs prefix-summed for the launch-time cut.
+    std::stable_sort(tiles.begin(), tiles.end(), [](const McsTile& a, const McsTile& b) { return a.cls > b.cls; });
+    long long* h_cum = static_cast<long long*>(malloc(sizeof(long long) * (n_tiles + 1)));
+    int2* d_sched = nullptr;
+    if (!h_cum) {
+        why(plan, "out of host memory");
+        cudaFree(d_tiles);
+        cudaFree(d_layers);
+        return;
+    }
+    h_cum[0] = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+        tiles[i].flags = (short)tile_cost(tiles[i]);
+        h_cum[i + 1] = h_cum[i] + tiles[i].flags;
+    }
+    plan->class_first[0] = 0;
+    plan->class_first[1] = plan->class_first[2] = plan->class_first[3] = n_tiles;
+    for (int i = n_tiles - 1; i >= 0; --i) {
+        if (tiles[i].cls != MCS_TILE_WARP) plan->class_first[1] = i;
+        if (tiles[i].cls == MCS_TILE_ZERO) plan->class_first[2] = i;
+    }
+    e = cudaMalloc(&d_sched, sizeof(int2) * MCS_SCHED_SLOTS * 3 * (MCS_SCHED_MAX_GRID + 1));
+    if (e == cudaSuccess) e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_layers, plan->layers, sizeof(McsLayer) * MCS_MAX_LAYERS, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         why(plan, "tile upload failed: %s", cudaGetErrorString(e));
         cudaFree(d_tiles);
         cudaFree(d_layers);
+        if (d_sched) cudaFree(d_sched);
+        free(h_cum);
         return;
     }
+    plan->h_cum = h_cum;
+    plan->d_sched = d_sched;
+    for (int i = 0; i < MCS_SCHED_SLOTS; ++i) plan->sched_frames[i] = plan->sched_grid[i] = 0;
+    plan->sched_next = 0;
     plan->d_tiles = d_tiles;
     plan->d_layers = d_layers;
     plan->n_tiles = n_tiles;
