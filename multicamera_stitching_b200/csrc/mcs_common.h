@@ -79,6 +79,7 @@ static_assert(sizeof(McsTile) == 32, "McsTile must stay 32 bytes");
 
 #define MCS_BOX_BYTES_MAX (40 * 1024)   // per staged source box
 
+#define MCS_FRAME_BLOCK_DEFAULT 32
 #define MCS_SCHED_SLOTS 4
 #define MCS_SCHED_MAX_GRID 2047
 
@@ -97,6 +98,8 @@ struct mcs_plan {
     int box_bytes;           // shared-memory bytes of one staging buffer (max over layers, 128-aligned)
     McsTile* d_tiles;
     McsLayer* d_layers;
+    uint32_t* d_desc;        // per-pixel descriptors of the WARP tiles, 2048 words per tile (mcs_tiles.cu)
+    int frame_block;         // frames per sweep of the tile table (mcs_launch_tiled)
     // cache of the TMA descriptors of the last call (keyed by the source table)
     unsigned char tmap_cache[MCS_MAX_LAYERS * 128 + 64];
     const void* cache_src[MCS_MAX_LAYERS];

@@ -70,6 +70,38 @@ mcs_tile_bounds_kernel(const McsTile* __restrict__ tiles, const McsLayer* __rest
     }
 }
 
+// One CTA of 256 threads per WARP tile: the frame-invariant sampling descriptor of each of its
+// 128 x 16 pixel slots, in the order the tiled kernel's threads read them ([j][warp][lane] with
+// row = warp + 8 * (j >> 2), column = lane + 32 * (j & 3)):
+//   bits 0..15   byte offset of tap (sx, sy) inside the tile's staged box
+//   bits 16..20  ax,  bits 21..25  ay   (1/32-px fractions)
+// sx / sy are clamped to [-2, src_w] / [-2, src_h] like in the bounds pass: at the clamp values
+// both taps of that axis read the zero fill of the box.  Slots the tile does not own get 0.
+__global__ void __launch_bounds__(256)
+mcs_tile_desc_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restrict__ layers, int channels,
+                     uint32_t* __restrict__ desc) {
+    const int t = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const McsTile tile = tiles[t];
+    const McsLayer& L = layers[tile.layer];
+    const double m0 = L.mi[0], m3 = L.mi[3], m6 = L.mi[6];
+    const int sp = L.bw4 * 4;
+    for (int j = 0; j < 8; ++j) {
+        const int row = warp + 8 * (j >> 2), col = lane + 32 * (j & 3);
+        uint32_t w = 0;
+        if (col >= tile.c0 && col < tile.c1 && row < tile.h) {
+            const int xl = tile.cx0 + col - L.ox, yl = tile.y0 + row - L.oy;
+            const RowBlock rb = row_block(L.mi, xl & ~63, yl);
+            int X, Y;
+            fixed_coords(m0, m3, m6, rb, xl & 63, X, Y);
+            const int sx = max(-2, min(L.src_w, sat16(X >> 5))), sy = max(-2, min(L.src_h, sat16(Y >> 5)));
+            const int b = (sy - tile.by) * sp + sx * channels - 4 * tile.bx;
+            w = (uint32_t)b | ((uint32_t)(X & 31) << 16) | ((uint32_t)(Y & 31) << 21);
+        }
+        desc[(size_t)t * (MCS_CELL_W * MCS_CELL_H) + (j * 8 + warp) * 32 + lane] = w;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -124,6 +156,8 @@ void mcs_plan_free_tiles(mcs_plan* plan) {
     if (plan->d_tiles) cudaFree(plan->d_tiles);
     if (plan->d_layers) cudaFree(plan->d_layers);
     if (plan->d_sched) cudaFree(plan->d_sched);
+    if (plan->d_desc) cudaFree(plan->d_desc);
+    plan->d_desc = nullptr;
     free(plan->h_cum);
     plan->d_tiles = nullptr;
     plan->d_layers = nullptr;
@@ -243,7 +277,11 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         if (bw4[k] == 0) { bw4[k] = 4; bh[k] = 1; }   // layer owns nothing that needs staging
         // box pitch a multiple of 128 bytes (32 banks): when the lanes of a warp straddle two
         // source rows their words still fall into disjoint shared-memory banks
-        bw4[k] = (bw4[k] + 31) & ~31;
+        {
+            const char* env = getenv("MCS_TILED_PITCH_WORDS");   // experiments: box pitch granularity
+            const int g = env && atoi(env) >= 4 ? atoi(env) : 32;
+            bw4[k] = (bw4[k] + g - 1) / g * g;
+        }
         if (bw4[k] > 256 || bh[k] > 256 || bw4[k] * 4 * bh[k] > MCS_BOX_BYTES_MAX) {
             why(plan, "layer %d needs a %d x %d byte source box per tile (limit 1024 x 256, %d bytes)", k,
                 bw4[k] * 4, bh[k], MCS_BOX_BYTES_MAX);
@@ -282,13 +320,33 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
     e = cudaMalloc(&d_sched, sizeof(int2) * MCS_SCHED_SLOTS * 3 * (MCS_SCHED_MAX_GRID + 1));
     if (e == cudaSuccess) e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_layers, plan->layers, sizeof(McsLayer) * MCS_MAX_LAYERS, cudaMemcpyHostToDevice);
+    // per-pixel descriptors of the WARP tiles (they come first in the sorted table)
+    uint32_t* d_desc = nullptr;
+    const int n_warp_tiles = plan->class_first[1];
+    if (e == cudaSuccess && n_warp_tiles > 0) {
+        e = cudaMalloc(&d_desc, sizeof(uint32_t) * MCS_CELL_W * MCS_CELL_H * (size_t)n_warp_tiles);
+        if (e == cudaSuccess) {
+            mcs_tile_desc_kernel<<<n_warp_tiles, 256>>>(d_tiles, d_layers, C, d_desc);
+            mcs_count_launch(1);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+    }
     if (e != cudaSuccess) {
         why(plan, "tile upload failed: %s", cudaGetErrorString(e));
         cudaFree(d_tiles);
         cudaFree(d_layers);
         if (d_sched) cudaFree(d_sched);
+        if (d_desc) cudaFree(d_desc);
         free(h_cum);
         return;
+    }
+    plan->d_desc = d_desc;
+    {
+        // frames per sweep of the tile table; $MCS_TILED_FRAME_BLOCK overrides (experiments)
+        const char* env = getenv("MCS_TILED_FRAME_BLOCK");
+        const int v = env ? atoi(env) : 0;
+        plan->frame_block = v > 0 ? v : MCS_FRAME_BLOCK_DEFAULT;
     }
     plan->h_cum = h_cum;
     plan->d_sched = d_sched;
