@@ -54,6 +54,19 @@ def build_chain(name):
     return synthetic_chain(n, h, w, 3, kind="smooth")
 
 
+def recorded_traffic(workload, batch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if the
+    capture was taken at another batch size or does not exist)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")) as f:
+            rec = json.load(f)[workload]
+        if int(rec["panoramas_per_launch"]) != int(batch):
+            return None
+        return int(rec["dram_read_bytes"]) + int(rec["dram_write_bytes"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -320,7 +333,9 @@ def run_ours(args, rank, local_rank, world):
                    "panorama_pitch_bytes": int(out.stride(1)), "kernel_variant": plan.handle.last_variant(),
                    "tiled_ctas_per_sm": plan.handle.tiled_ctas_per_sm()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": recorded_traffic(args.workload, batch),
+                     "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r1_dram_traffic.json",
+                     "algorithmic_bytes_per_launch": algo_bytes * batch, "peak_source": peak_src,
                      "algorithmic_bytes_per_panorama": algo_bytes,
                      "launch_ms": launch_ms, "panoramas_per_launch": batch},
         "cpu_baseline": cpu,
