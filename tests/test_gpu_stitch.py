@@ -264,3 +264,45 @@ def test_full_size_config3_vs_cv2(cuda_device):
     l0 = st.plan([images[l].shape for l in labels], cuda_device).flat.layers[0]
     x0, y0, x1, y1 = l0.rect
     assert np.array_equal(got[y0:y1, x0:x1], images[labels[0]][y0 - l0.oy:y1 - l0.oy, x0 - l0.ox:x1 - l0.ox])
+
+
+@pytest.mark.parametrize("frame_block,n_frames,pitch_align", [
+    (1, 5, 1), (4, 11, 128), (4, 8, 1), (32, 11, 128), (3, 7, 32),
+])
+def test_tiled_variant_frame_blocks(cuda_device, monkeypatch, frame_block, n_frames, pitch_align):
+    """The work split of the tiled kernel: frame blocks (last one shorter), round-robin cells plus
+    leftover runs, padded and dense panorama pitch - every frame of the batch must equal the cv2
+    chain on that frame's inputs."""
+    monkeypatch.setenv("MCS_TILED_FRAME_BLOCK", str(frame_block))
+    st, states, labels, images = synthetic_chain(6, 270, 480, 3, kind="noise", xoffset=4, yoffset=9)
+    sets = [synthetic_chain(6, 270, 480, 3, kind="noise", frame_index=f)[3] for f in range(n_frames)]
+    batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.tiled_status() == "", plan.handle.tiled_status()
+    out = plan.new_output(n_frames, pitch_align=pitch_align)
+    out.fill_(0xCD)
+    plan.handle.force_variant(2)
+    try:
+        st.stitch_batch(batch, out=out)
+        assert plan.handle.last_variant() == 2
+    finally:
+        plan.handle.force_variant(0)
+    got = out.cpu().numpy()
+    for f in range(n_frames):
+        _check(got[f], stitcher_ref.stitch_chain(states, labels, sets[f]))
+
+
+def test_batch_equals_single_frames_config2(cuda_device):
+    """Size-independent property at BASELINE config 2's full size: a batched launch (several
+    frames per chunk, leftover runs split between CTAs) gives, frame by frame, exactly what
+    one-frame launches give."""
+    st, states, labels, images = synthetic_chain(6, 1080, 1920, 3, kind="smooth")
+    sets = [synthetic_chain(6, 1080, 1920, 3, kind="smooth", frame_index=f)[3] for f in range(3)]
+    batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    out = st.stitch_batch(batch, out=plan.new_output(3, pitch_align=128))
+    assert plan.handle.last_variant() == 2
+    for f in range(3):
+        single = st.stitch({l: batch[l][f] for l in labels})
+        assert torch.equal(out[f], single)
+    _check(out[0].cpu().numpy(), stitcher_ref.stitch_chain(states, labels, sets[0]))
