@@ -115,8 +115,19 @@ int mcs_stitch_u8(const mcs_plan* plan, const uint8_t* const* src,
                   int n_frames, uint8_t* dst, int64_t dst_pitch_bytes,
                   int64_t dst_frame_stride, void* cuda_stream);
 
+/*
+ * mcs_plan_set_feather - blend mode of the plan.  feather_log2 = 0 (default) is the
+ * reference's rectangle overwrite (StitcherClass.py:240-241).  feather_log2 = n > 0 softens
+ * every paste over F = 2^n pixels inside the pasted rectangle: with a = min(F, 1 + distance to
+ * the nearest rectangle edge), a pixel there becomes (a*inner + (F-a)*warped + F/2) >> n where
+ * the warped camera has a tap inside its source.  Extension with no reference counterpart
+ * (SURVEY.md section 8 row f1); specification in oracle/feather_model.py.  Not supported for
+ * plans with super-mode crops.
+ */
+int mcs_plan_set_feather(mcs_plan* plan, int feather_log2);
+
 /* Which kernel variant the last mcs_stitch_u8 on this plan launched
- * (diagnostics for tests / bench): 0 = none yet, 1 = gather, 2 = tiled. */
+ * (diagnostics for tests / bench): 0 = none yet, 1 = gather, 2 = tiled, 3 = feather. */
 int mcs_plan_last_variant(const mcs_plan* plan);
 
 /* Pin the kernel variant of a plan: 0 = automatic (tiled when the plan and the buffers allow

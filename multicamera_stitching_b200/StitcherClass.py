@@ -65,6 +65,9 @@ class Stitcher(Debugger):
             self.stitcher_labels.append("({}&{})".format(left, self.img_labels[idx + 1]))
         self.stitchers = [StitcherBase(sid=label, super_mode=super_mode)
                           for label in self.stitcher_labels]
+        # Blend mode (extension; the reference only overwrites, :240-241): 0 = overwrite, n > 0 =
+        # feather every paste over 2**n pixels (include/mcs.h mcs_plan_set_feather).
+        self.feather_log2 = 0
 
     # -- engine plumbing (never pickled) -------------------------------------
     def _engine_(self):
@@ -129,7 +132,8 @@ class Stitcher(Debugger):
         if len(self.img_labels) < 2:
             return images_dic[self.img_labels[-1]]
         frames = [images_dic[label] for label in self.img_labels]
-        out = _composite(self._engine_(), self.stitchers, frames, batched=False, debugger=self)
+        out = _composite(self._engine_(), self.stitchers, frames, batched=False, debugger=self,
+                         feather_log2=getattr(self, "feather_log2", 0))
         if draw_descriptors and not _is_tensor(out):
             # the reference draws every stage's overlay into the canvas it produced (:244-245);
             # only the last stage's overlay is in final-panorama coordinates
@@ -141,11 +145,13 @@ class Stitcher(Debugger):
         uint8 CUDA tensor ``[F, H, W, C]``; returns (or fills ``out``) a CUDA
         tensor ``[F, H_out, W_out, C]``.  Extension of the reference API."""
         frames = [frames_dic[label] for label in self.img_labels]
-        return _composite(self._engine_(), self.stitchers, frames, batched=True, out=out, debugger=self)
+        return _composite(self._engine_(), self.stitchers, frames, batched=True, out=out, debugger=self,
+                          feather_log2=getattr(self, "feather_log2", 0))
 
     def plan(self, img_shapes, device=None):
         """Compiled plan (``engine.CompiledPlan``) for frames of these shapes."""
-        return self._engine_().plan_for(self.stitchers, [tuple(s) for s in img_shapes], device)
+        return self._engine_().plan_for(self.stitchers, [tuple(s) for s in img_shapes], device,
+                                        feather_log2=getattr(self, "feather_log2", 0))
 
     # -- persistence -----------------------------------------------------------
     def save_stitcher(self, save_path):
@@ -385,7 +391,7 @@ class StitcherBase(Debugger):
 
 
 # ---------------------------------------------------------------------------
-def _composite(engine, stages, frames, batched, out=None, debugger=None):
+def _composite(engine, stages, frames, batched, out=None, debugger=None, feather_log2=0):
     """Run the fused kernel for this chain on these frames."""
     import torch  # local: keeps `import StitcherClass` cheap for calibration-only users
 
@@ -393,7 +399,7 @@ def _composite(engine, stages, frames, batched, out=None, debugger=None):
     shapes = [_shape_of(f)[1:] if batched else _shape_of(f) for f in frames]
     device = frames[0].device if on_device else None
     try:
-        plan = engine.plan_for(stages, shapes, device)
+        plan = engine.plan_for(stages, shapes, device, feather_log2=feather_log2)
     except PlanUnsupported as e:
         if debugger is not None:
             debugger.debugger(DEBUG_LEVEL_0, "[STITCHER] {}".format(e), log_type="err")

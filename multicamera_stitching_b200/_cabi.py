@@ -21,7 +21,8 @@ ABI_VERSION = 1
 # every symbol include/mcs.h declares
 EXPORTS = (
     "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_destroy",
-    "mcs_plan_owned_pixels", "mcs_stitch_u8", "mcs_plan_last_variant", "mcs_plan_force_variant",
+    "mcs_plan_owned_pixels", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_last_variant",
+    "mcs_plan_force_variant",
     "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_launch_count",
     "mcs_match_hamming_top2", "mcs_ransac_homography",
 )
@@ -74,6 +75,8 @@ def load(build_if_missing=False):
     lib.mcs_plan_last_variant.argtypes = [_vp]
     lib.mcs_plan_force_variant.restype = ctypes.c_int
     lib.mcs_plan_force_variant.argtypes = [_vp, ctypes.c_int]
+    lib.mcs_plan_set_feather.restype = ctypes.c_int
+    lib.mcs_plan_set_feather.argtypes = [_vp, ctypes.c_int]
     lib.mcs_plan_tiled_ctas_per_sm.restype = ctypes.c_int
     lib.mcs_plan_tiled_ctas_per_sm.argtypes = [_vp]
     lib.mcs_plan_tiled_status.restype = ctypes.c_char_p
@@ -164,6 +167,9 @@ class Plan(object):
     def force_variant(self, variant):
         """0 = automatic, 1 = gather kernel, 2 = tiled (TMA-staged) kernel."""
         check(_lib.mcs_plan_force_variant(self._h, int(variant)), "mcs_plan_force_variant")
+
+    def set_feather(self, feather_log2):
+        check(_lib.mcs_plan_set_feather(self._h, int(feather_log2)), "mcs_plan_set_feather")
 
     def tiled_ctas_per_sm(self):
         return int(_lib.mcs_plan_tiled_ctas_per_sm(self._h))

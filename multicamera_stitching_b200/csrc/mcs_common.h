@@ -90,6 +90,7 @@ struct mcs_plan {
     int device;
     McsLayer layers[MCS_MAX_LAYERS];
     int last_variant;
+    int feather_log2;        // 0 = the reference's overwrite paste, > 0 = feather blend over 2^n pixels
     int force_variant;       // 0 = automatic, 1 = gather, 2 = tiled (diagnostics)
     // tiled variant
     int tiled_ok;            // tile table built and every box within limits

@@ -164,3 +164,23 @@ extern "C" const char* mcs_plan_tiled_status(const mcs_plan* plan) {
 }
 
 extern "C" int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan) { return plan ? plan->grid_ctas_per_sm : 0; }
+
+extern "C" int mcs_plan_set_feather(mcs_plan* plan, int feather_log2) {
+    MCS_CHECK_ARG(plan != nullptr, "mcs_plan_set_feather: plan is NULL");
+    MCS_CHECK_ARG(feather_log2 >= 0 && feather_log2 <= 12, "mcs_plan_set_feather: feather_log2=%d outside 0..12",
+                  feather_log2);
+    if (feather_log2 > 0) {
+        // the blend walks the nested rectangles: they must be nested and unclipped
+        for (int k = 1; k < plan->n_layers; ++k) {
+            const McsLayer& o = plan->layers[k];
+            const McsLayer& i = plan->layers[k - 1];
+            const bool empty_i = i.rx1 <= i.rx0 || i.ry1 <= i.ry0;
+            if (!empty_i && (o.rx0 > i.rx0 || o.ry0 > i.ry0 || o.rx1 < i.rx1 || o.ry1 < i.ry1)) {
+                mcs_set_error("mcs_plan_set_feather: layer rectangles are not nested (layer %d)", k);
+                return MCS_ERR_UNSUPPORTED;
+            }
+        }
+    }
+    plan->feather_log2 = feather_log2;
+    return MCS_OK;
+}

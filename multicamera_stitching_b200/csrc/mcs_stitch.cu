@@ -160,6 +160,65 @@ mcs_stitch_gather_kernel(const __grid_constant__ StitchArgs a, unsigned long lon
 }
 
 // --------------------------------------------------------------------------------------------
+// Feather blend mode (extension; the reference has only the overwrite
+// of StitcherClass.py:240-241).  Specification: oracle/feather_model.py.  The chain's nested
+// pastes are softened over F = 2^feather_log2 pixels inside every pasted rectangle:
+//   value = sample of the innermost layer m whose rectangle contains the pixel
+//   for k = m+1 .. n-1:   a = min(F, 1 + distance to the nearest edge of rectangle k-1)
+//       a == F -> done (rectangles are nested, the distance only grows)
+//       layer k touched here -> value = (a*value + (F-a)*sample_k + F/2) >> feather_log2
+// Every stage rounds to uint8 like the chain it models.  One thread per output pixel of a row
+// quad; taps straight from global memory (this mode is not the measured hot path).
+template <int C>
+__device__ __forceinline__ bool sample_layer(const LayerArgs& L, int frame, int x, int y, int (&v)[C]) {
+    const int xl = x - L.g.ox, yl = y - L.g.oy;
+    const uint8_t* src = L.src + (long long)frame * L.frame_stride;
+    if (L.g.kind == MCS_LAYER_COPY) {
+        load_px<C>(src + (long long)yl * L.pitch + (long long)xl * C, v);
+        return true;
+    }
+    const RowBlock rb = row_block(L.g.mi, xl & ~63, yl);
+    int X, Y;
+    fixed_coords(L.g.mi[0], L.g.mi[3], L.g.mi[6], rb, xl & 63, X, Y);
+    return sample_u8<C>(src, L.pitch, L.g.src_w, L.g.src_h, X, Y, v);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+mcs_stitch_feather_kernel(const __grid_constant__ StitchArgs a, int feather_log2) {
+    const int x_first = blockIdx.x * MCS_TILE_W + threadIdx.x * 4;
+    const int y = blockIdx.y * MCS_TILE_H + threadIdx.y;
+    if (y >= a.out_h || x_first >= a.out_w) return;
+    const int frame = blockIdx.z;
+    const int F = 1 << feather_log2;
+    const int n_px = min(4, a.out_w - x_first);
+    uint8_t* out = a.dst + (long long)frame * a.dst_frame_stride + (long long)y * a.dst_pitch +
+                   (long long)x_first * C;
+    for (int i = 0; i < n_px; ++i) {
+        const int x = x_first + i;
+        int v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = 0;
+        const int m = find_owner(a, x, y);
+        if (m >= 0) {
+            sample_layer<C>(a.L[m], frame, x, y, v);
+            for (int k = m + 1; k < a.n_layers; ++k) {
+                const McsLayer& in = a.L[k - 1].g;   // the rectangle pasted at stage k
+                const int d = min(min(x - in.rx0, in.rx1 - 1 - x), min(y - in.ry0, in.ry1 - 1 - y)) + 1;
+                if (d >= F) break;
+                int w[C];
+                if (sample_layer<C>(a.L[k], frame, x, y, w)) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) v[c] = (d * v[c] + (F - d) * w[c] + (F >> 1)) >> feather_log2;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[i * C + c] = (uint8_t)v[c];
+    }
+}
+
+// --------------------------------------------------------------------------------------------
 static int fill_args(const mcs_plan* plan, StitchArgs& a, const uint8_t* const* src,
                      const int64_t* src_pitch, const int64_t* src_frame_stride, int n_frames,
                      uint8_t* dst, int64_t dst_pitch, int64_t dst_frame_stride) {
@@ -214,6 +273,22 @@ extern "C" int mcs_stitch_u8(const mcs_plan* plan_c, const uint8_t* const* src,
                       "mcs_stitch_u8: source %d pitch %lld < row bytes", k, (long long)src_pitch_bytes[k]);
     }
     cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (plan->feather_log2 > 0) {
+        StitchArgs fa;
+        fill_args(plan, fa, src, src_pitch_bytes, src_frame_stride, n_frames, dst, dst_pitch_bytes,
+                  dst_frame_stride);
+        dim3 block(MCS_TILE_W / 4, MCS_TILE_H, 1);
+        dim3 grid((plan->out_w + MCS_TILE_W - 1) / MCS_TILE_W, (plan->out_h + MCS_TILE_H - 1) / MCS_TILE_H, n_frames);
+        switch (plan->channels) {
+            case 1: mcs_stitch_feather_kernel<1><<<grid, block, 0, stream>>>(fa, plan->feather_log2); break;
+            case 3: mcs_stitch_feather_kernel<3><<<grid, block, 0, stream>>>(fa, plan->feather_log2); break;
+            default: mcs_stitch_feather_kernel<4><<<grid, block, 0, stream>>>(fa, plan->feather_log2); break;
+        }
+        mcs_count_launch(1);
+        MCS_CHECK_CUDA(cudaGetLastError());
+        plan->last_variant = 3;
+        return MCS_OK;
+    }
     const int force = plan->force_variant;
     const char* blocker = mcs_tiled_blocker(plan, src, src_pitch_bytes, src_frame_stride, n_frames, dst_pitch_bytes);
     if (force == 2 && blocker) {

@@ -9,7 +9,11 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .plan import flatten_chain, plan_tables, stage_signature
+from .plan import PlanUnsupported, flatten_chain, plan_tables, stage_signature
+
+
+def _stage_field(st, name):
+    return st[name] if isinstance(st, dict) else getattr(st, name)
 
 
 def _round_up(v, m):
@@ -19,12 +23,15 @@ def _round_up(v, m):
 class CompiledPlan(object):
     """A flattened chain plus its ``mcs_plan`` on one device."""
 
-    def __init__(self, flat, device):
+    def __init__(self, flat, device, feather_log2=0):
         self.flat = flat
         self.device = torch.device(device)
+        self.feather_log2 = int(feather_log2)
         with torch.cuda.device(self.device):
             kind, src_hw, fwd, origin, rect = plan_tables(flat)
             self.handle = _cabi.Plan(kind, src_hw, fwd, origin, rect, flat.out_w, flat.out_h, flat.channels)
+            if self.feather_log2:
+                self.handle.set_feather(self.feather_log2)
         self.cams = [l.cam for l in flat.layers]
         self.out_w, self.out_h, self.channels = flat.out_w, flat.out_h, flat.channels
 
@@ -118,7 +125,7 @@ class CompositeEngine(object):
             self._device = torch.device("cuda", torch.cuda.current_device())
         return torch.device(self._device)
 
-    def plan_for(self, stages, cam_shapes, device=None):
+    def plan_for(self, stages, cam_shapes, device=None, feather_log2=0):
         """Compiled plan for this chain state and these frame shapes, or None
         when no stage is calibrated (decided on the host, no device needed)."""
         shapes = tuple(tuple(int(v) for v in s) for s in cam_shapes)
@@ -126,12 +133,16 @@ class CompositeEngine(object):
         if all(s is None for s in sig):
             return None
         device = torch.device(device) if device is not None else self.device
-        key = (str(device), shapes, sig)
+        feather_log2 = int(feather_log2 or 0)
+        key = (str(device), shapes, sig, feather_log2)
         if key not in self._plans:
             flat = flatten_chain(stages, shapes)
+            if feather_log2 and any(_stage_field(st, "super_mode") and _stage_field(st, "cachedAH") is not None
+                                    for st in stages):
+                raise PlanUnsupported("the feather blend does not support super_mode crops")
             if len(self._plans) > 8:
                 self._plans.clear()
-            self._plans[key] = CompiledPlan(flat, device) if flat is not None else None
+            self._plans[key] = CompiledPlan(flat, device, feather_log2) if flat is not None else None
         return self._plans[key]
 
     def upload(self, cam, arr, device):

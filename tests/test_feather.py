@@ -1,0 +1,69 @@
+"""Feather blend mode (an extension the reference does not have):
+the numpy specification reduces to the reference's overwrite, and the CUDA kernel matches the
+specification bit for bit."""
+import numpy as np
+import pytest
+
+from helpers import synthetic_chain
+from oracle import feather_model, stitcher_ref
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 64, 96, 3), (3, 120, 200, 3), (4, 90, 160, 1)])
+def test_feather_width_one_is_the_reference_overwrite(n, h, w, c):
+    st, states, labels, images = synthetic_chain(n, h, w, c, kind="noise", xoffset=3, yoffset=5)
+    assert np.array_equal(feather_model.feather_chain(states, labels, images, 0),
+                          stitcher_ref.stitch_chain(states, labels, images))
+
+
+def test_feather_only_touches_the_seam_band():
+    st, states, labels, images = synthetic_chain(3, 120, 200, 3, kind="noise")
+    hard = stitcher_ref.stitch_chain(states, labels, images)
+    soft = feather_model.feather_chain(states, labels, images, 3)
+    assert soft.shape == hard.shape
+    changed = (soft != hard).any(axis=2)
+    assert changed.any()
+    # camera 0 keeps its pixels further than 8 px (+ one stage of nesting) from its border
+    bx = sum(int(s["Bpts"][0][0]) for s in states)
+    by = sum(int(s["Bpts"][0][1]) for s in states)
+    h, w = images[labels[0]].shape[:2]
+    assert not changed[by + 8:by + h - 8, bx + 8:bx + w - 8].any()
+
+
+def test_feather_rejects_super_mode():
+    st, states, labels, images = synthetic_chain(3, 120, 200, 3, super_mode=True)
+    with pytest.raises(ValueError):
+        feather_model.feather_chain(states, labels, images, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,h,w,c,log2", [
+    (2, 64, 96, 3, 2), (3, 120, 200, 3, 3), (4, 90, 160, 1, 4), (4, 90, 160, 4, 1), (6, 270, 480, 3, 5),
+])
+def test_feather_kernel_matches_specification(cuda_device, n, h, w, c, log2):
+    import torch
+    st, states, labels, images = synthetic_chain(n, h, w, c, kind="noise", xoffset=2, yoffset=7)
+    st.feather_log2 = log2
+    ref = feather_model.feather_chain(states, labels, images, log2)
+    got = st.stitch(images)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref), int(np.abs(got.astype(int) - ref.astype(int)).max())
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.last_variant() == 3
+    # batched, device-resident
+    sets = [synthetic_chain(n, h, w, c, kind="noise", frame_index=f)[3] for f in range(3)]
+    batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
+    out = st.stitch_batch(batch).cpu().numpy()
+    for f in range(3):
+        assert np.array_equal(out[f], feather_model.feather_chain(states, labels, sets[f], log2))
+    # width one = the reference's overwrite through the regular kernels
+    st.feather_log2 = 0
+    assert np.array_equal(st.stitch(images), stitcher_ref.stitch_chain(states, labels, images))
+
+
+@pytest.mark.gpu
+def test_feather_refuses_super_mode_plans(cuda_device):
+    from multicamera_stitching_b200.plan import PlanUnsupported
+    st, states, labels, images = synthetic_chain(3, 120, 200, 3, super_mode=True)
+    st.feather_log2 = 2
+    with pytest.raises(PlanUnsupported):
+        st.stitch(images)
