@@ -120,6 +120,38 @@ def golden_match():
     np.savez_compressed(os.path.join(OUT, "match_cv2.npz"), fa=fa, fb=fb, idx=idx, dist=dist, matches=matches)
 
 
+def recorded_csv_text():
+    """A small, well-formed data.csv in the capture node's format (two captures, three cameras)."""
+    rows = [["capture_id", "timestamp", "camera_label", "image_file"]]
+    for cap, n in ((0, 4), (1, 3)):
+        for i in range(n):
+            ts = 1565270000000 + 1000 * cap + 33 * i
+            for cam in ("C", "LL", "RR"):
+                rows.append([cap, ts, cam, "ab%02d-%d_%s.jpg" % (cap, ts, cam)])
+    return "\n".join(",".join(str(v) for v in r) for r in rows) + "\n"
+
+
+def golden_recorded(ref_root):
+    """The reference's own reader (MediaPlayer/model.py) on that file."""
+    import importlib.util
+    import json
+    import tempfile
+    spec = importlib.util.spec_from_file_location("ref_model", os.path.join(ref_root, "MediaPlayer", "model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    text = recorded_csv_text()
+    with open(os.path.join(OUT, "recorded_data.csv"), "w") as f:
+        f.write(text)
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "data.csv"), "w") as f:
+            f.write(text)
+        r = mod.data_reader()
+        r.load_data(d)
+    with open(os.path.join(OUT, "recorded_reference.json"), "w") as f:
+        json.dump({"camera_labels": r.camera_labels, "timestamps": r.timestamps, "images": r.images,
+                   "line_count": r.line_count}, f, indent=1)
+
+
 if __name__ == "__main__":
     ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -127,10 +159,13 @@ if __name__ == "__main__":
     golden_warp()
     golden_chain()
     golden_match()
+    golden_recorded(ref_root)
     with open(os.path.join(OUT, "README.md"), "w") as f:
         f.write("Fixtures written by scripts/make_golden.py (cv2 %s, numpy %s).\n"
                 "utils_reference.npz comes from the reference's own Calibration_Utils/Utils.py;\n"
-                "the others from cv2 driven as PostScripts/Stitcher/StitcherClass.py drives it.\n"
+                "recorded_reference.json is what the reference's MediaPlayer/model.py data_reader parses from\n"
+                "recorded_data.csv; the others come from cv2 driven as PostScripts/Stitcher/StitcherClass.py\n"
+                "drives it.\n"
                 % (cv2.__version__, np.__version__))
     for n in sorted(os.listdir(OUT)):
         print(n, os.path.getsize(os.path.join(OUT, n)))
