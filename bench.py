@@ -127,8 +127,22 @@ class ClockSampler(object):
             os.unlink(self.path)
         except Exception:
             pass
+        self.sm, self.mx, self.reasons = sm, mx, reasons
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+    @staticmethod
+    def merged(*samplers):
+        """One clocks record over the timed regions of several samplers."""
+        sm, mx, reasons = [], [], set()
+        for s in samplers:
+            sm += getattr(s, "sm", [])
+            mx += getattr(s, "mx", [])
+            reasons |= getattr(s, "reasons", set())
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(reasons), "samples": len(sm)}
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx))
         return out
 
 
@@ -203,13 +217,14 @@ def run_ours(args, rank, local_rank, world):
     import torch
     from multicamera_stitching_b200 import _cabi
     from multicamera_stitching_b200.sequence import SequencePipeline, pinned_like
-    from multicamera_stitching_b200.shard import ShardContext
+    from multicamera_stitching_b200.shard import ShardContext, bind_to_gpu_numa
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the GPU arm)")
     _cabi.load()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_bound = bind_to_gpu_numa(local_rank)   # pinned buffers of this rank on its GPU's socket
     ctx = ShardContext.from_env(backend="nccl", device=device)   # control path only: barrier + max time
     barrier = ctx.barrier
     max_over_ranks = ctx.max_over_ranks
@@ -298,12 +313,18 @@ def run_ours(args, rank, local_rank, world):
         if int(d.max()) > 1:
             raise SystemExit("bench.py: e2e panorama differs from the cv2 chain")
     e2e_steps = max(3, min(args.steps, 10))
+    sampler2 = ClockSampler(local_rank)
+    if rank == 0:
+        sampler2.start()
     e0.record()
     for _ in range(e2e_steps):
         pipe.run(host_frames, host_out)
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    if rank == 0:
+        sampler2.stop()
+        clocks = ClockSampler.merged(sampler, sampler2)   # both timed regions
     e2e_pps = world * e2e_batch * e2e_steps / (e2e_ms * 1e-3)
 
     # ---- CPU baseline (rank 0, N = 1 only): the reference's cv2 chain ----------------
@@ -341,7 +362,8 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_pps, "unit": "panoramas/s", "h2d_bytes_per_step": h2d_b * e2e_batch,
                 "d2h_bytes_per_step": d2h_b * e2e_batch, "steps": e2e_steps,
-                "ms_per_step": e2e_ms / e2e_steps, "api": "sequence.SequencePipeline.run (pinned host in/out)"},
+                "ms_per_step": e2e_ms / e2e_steps, "api": "sequence.SequencePipeline.run (pinned host in/out)",
+                "numa_bound": bool(numa_bound)},
         "gpu_launches": launches,
         "clocks": clocks,
         "parity": parity,

@@ -15,6 +15,21 @@ import torch.distributed as dist
 from .sequence import shard_range
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin the calling thread to the CPUs closest to GPU ``device_index`` (NVML's ideal affinity),
+    so that the pinned host buffers it allocates next live on that GPU's NUMA node and every
+    rank's host<->device traffic stays on its own socket.  Best effort: returns False when NVML
+    is missing or refuses."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:
+        return False
+
+
 class ShardContext(object):
     """Rank / world size of this process plus the three collectives the path needs."""
 
