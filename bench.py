@@ -4,9 +4,9 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A *step* is one pass of the hot path over one batch of synthetic frame-sets
-(default: BASELINE.json config 2, 6 x 1080p cameras, a batch of 32 frame-sets
-resident in HBM, ~1.2 GB of input per step so consecutive steps never see a
-warm L2).  Rank 0 prints ONE JSON line:
+(default: BASELINE.json config 2, 6 x 1080p cameras, a batch of 64 frame-sets
+resident in HBM, ~2.4 GB of input per step so consecutive steps never see a
+warm L2; the end-to-end leg moves 32 frame-sets per step).  Rank 0 prints ONE JSON line:
 
   value     panoramas/s, whole job, inputs already resident in HBM
   e2e       the same metric through the host-facing sequence API: pinned host
@@ -41,7 +41,7 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # name: (n_cams, H, W, batch of frame-sets per step, e2e frame-sets per step)
     "cfg1_3x720p": (3, 720, 1280, 64, 64),
-    "cfg2_6x1080p": (6, 1080, 1920, 32, 32),
+    "cfg2_6x1080p": (6, 1080, 1920, 64, 32),
     "cfg3_8x2160p": (8, 2160, 3840, 8, 8),
 }
 FALLBACK_HBM_GBS = 6650.0
@@ -224,7 +224,8 @@ def run_ours(args, rank, local_rank, world):
     _cabi.load()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    numa_bound = bind_to_gpu_numa(local_rank)   # pinned buffers of this rank on its GPU's socket
+    # pinned buffers of this rank on its GPU's socket ($MCS_BENCH_NO_NUMA=1 leaves the threads alone)
+    numa_bound = False if os.environ.get("MCS_BENCH_NO_NUMA") else bind_to_gpu_numa(local_rank)
     ctx = ShardContext.from_env(backend="nccl", device=device)   # control path only: barrier + max time
     barrier = ctx.barrier
     max_over_ranks = ctx.max_over_ranks
