@@ -91,6 +91,10 @@ struct mcs_plan {
     McsLayer layers[MCS_MAX_LAYERS];
     int last_variant;
     int feather_log2;        // 0 = the reference's overwrite paste, > 0 = feather blend over 2^n pixels
+    int4* d_strips;          // feather: band strips {x0, y0, x1, y1} inside the pasted rectangles
+    long long* d_strip_prefix;   // n_strips + 1 running pixel counts
+    int n_strips;
+    long long strip_pixels;
     int force_variant;       // 0 = automatic, 1 = gather, 2 = tiled (diagnostics)
     // tiled variant
     int tiled_ok;            // tile table built and every box within limits

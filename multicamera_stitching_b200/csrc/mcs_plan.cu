@@ -145,6 +145,8 @@ extern "C" int mcs_plan_create(mcs_plan** out, int n_layers, int channels,
 
 extern "C" int mcs_plan_destroy(mcs_plan* plan) {
     if (!plan) return MCS_OK;
+    if (plan->d_strips) cudaFree(plan->d_strips);
+    if (plan->d_strip_prefix) cudaFree(plan->d_strip_prefix);
     mcs_plan_free_tiles(plan);
     delete plan;
     return MCS_OK;
@@ -165,21 +167,72 @@ extern "C" const char* mcs_plan_tiled_status(const mcs_plan* plan) {
 
 extern "C" int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan) { return plan ? plan->grid_ctas_per_sm : 0; }
 
+static void free_strips(mcs_plan* plan) {
+    if (plan->d_strips) cudaFree(plan->d_strips);
+    if (plan->d_strip_prefix) cudaFree(plan->d_strip_prefix);
+    plan->d_strips = nullptr;
+    plan->d_strip_prefix = nullptr;
+    plan->n_strips = 0;
+    plan->strip_pixels = 0;
+}
+
 extern "C" int mcs_plan_set_feather(mcs_plan* plan, int feather_log2) {
     MCS_CHECK_ARG(plan != nullptr, "mcs_plan_set_feather: plan is NULL");
     MCS_CHECK_ARG(feather_log2 >= 0 && feather_log2 <= 12, "mcs_plan_set_feather: feather_log2=%d outside 0..12",
                   feather_log2);
-    if (feather_log2 > 0) {
-        // the blend walks the nested rectangles: they must be nested and unclipped
-        for (int k = 1; k < plan->n_layers; ++k) {
-            const McsLayer& o = plan->layers[k];
-            const McsLayer& i = plan->layers[k - 1];
-            const bool empty_i = i.rx1 <= i.rx0 || i.ry1 <= i.ry0;
-            if (!empty_i && (o.rx0 > i.rx0 || o.ry0 > i.ry0 || o.rx1 < i.rx1 || o.ry1 < i.ry1)) {
-                mcs_set_error("mcs_plan_set_feather: layer rectangles are not nested (layer %d)", k);
-                return MCS_ERR_UNSUPPORTED;
-            }
+    free_strips(plan);
+    plan->feather_log2 = 0;
+    if (feather_log2 == 0) return MCS_OK;
+    // the blend walks the nested rectangles: they must be nested
+    for (int k = 1; k < plan->n_layers; ++k) {
+        const McsLayer& o = plan->layers[k];
+        const McsLayer& i = plan->layers[k - 1];
+        const bool empty_i = i.rx1 <= i.rx0 || i.ry1 <= i.ry0;
+        if (!empty_i && (o.rx0 > i.rx0 || o.ry0 > i.ry0 || o.rx1 < i.rx1 || o.ry1 < i.ry1)) {
+            mcs_set_error("mcs_plan_set_feather: layer rectangles are not nested (layer %d)", k);
+            return MCS_ERR_UNSUPPORTED;
         }
+    }
+    // Band strips: inside the rectangle pasted at stage k (that of layer k-1), the pixels closer
+    // than F - 1 to its border: top and bottom strips over the full width, left and right strips
+    // over the rows between them.
+    const int F = 1 << feather_log2, B = F - 1;
+    int4 strips[4 * MCS_MAX_LAYERS];
+    long long prefix[4 * MCS_MAX_LAYERS + 1];
+    int n = 0;
+    prefix[0] = 0;
+    auto add = [&](int x0, int y0, int x1, int y1) {
+        if (x1 > x0 && y1 > y0) {
+            strips[n] = make_int4(x0, y0, x1, y1);
+            prefix[n + 1] = prefix[n] + (long long)(x1 - x0) * (y1 - y0);
+            ++n;
+        }
+    };
+    for (int k = 1; k < plan->n_layers && B > 0; ++k) {
+        const McsLayer& r = plan->layers[k - 1];
+        if (r.rx1 <= r.rx0 || r.ry1 <= r.ry0) continue;
+        const int yt = r.ry0 + B < r.ry1 ? r.ry0 + B : r.ry1;          // end of the top strip
+        const int yb = r.ry1 - B > yt ? r.ry1 - B : yt;                  // start of the bottom strip
+        add(r.rx0, r.ry0, r.rx1, yt);
+        add(r.rx0, yb, r.rx1, r.ry1);
+        const int xl = r.rx0 + B < r.rx1 ? r.rx0 + B : r.rx1;
+        const int xr = r.rx1 - B > xl ? r.rx1 - B : xl;
+        add(r.rx0, yt, xl, yb);
+        add(xr, yt, r.rx1, yb);
+    }
+    if (n > 0) {
+        cudaError_t e = cudaMalloc(&plan->d_strips, sizeof(int4) * n);
+        if (e == cudaSuccess) e = cudaMalloc(&plan->d_strip_prefix, sizeof(long long) * (n + 1));
+        if (e == cudaSuccess) e = cudaMemcpy(plan->d_strips, strips, sizeof(int4) * n, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(plan->d_strip_prefix, prefix, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            free_strips(plan);
+            mcs_set_error("mcs_plan_set_feather: %s", cudaGetErrorString(e));
+            return MCS_ERR_CUDA;
+        }
+        plan->n_strips = n;
+        plan->strip_pixels = prefix[n];
     }
     plan->feather_log2 = feather_log2;
     return MCS_OK;

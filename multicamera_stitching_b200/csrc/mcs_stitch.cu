@@ -167,8 +167,8 @@ mcs_stitch_gather_kernel(const __grid_constant__ StitchArgs a, unsigned long lon
 //   for k = m+1 .. n-1:   a = min(F, 1 + distance to the nearest edge of rectangle k-1)
 //       a == F -> done (rectangles are nested, the distance only grows)
 //       layer k touched here -> value = (a*value + (F-a)*sample_k + F/2) >> feather_log2
-// Every stage rounds to uint8 like the chain it models.  One thread per output pixel of a row
-// quad; taps straight from global memory (this mode is not the measured hot path).
+// Every stage rounds to uint8 like the chain it models.  Taps straight from global memory: only
+// the seam bands are evaluated this way (mcs_feather_band_kernel below).
 template <int C>
 __device__ __forceinline__ bool sample_layer(const LayerArgs& L, int frame, int x, int y, int (&v)[C]) {
     const int xl = x - L.g.ox, yl = y - L.g.oy;
@@ -183,39 +183,51 @@ __device__ __forceinline__ bool sample_layer(const LayerArgs& L, int frame, int 
     return sample_u8<C>(src, L.pitch, L.g.src_w, L.g.src_h, X, Y, v);
 }
 
+// Feathered value of one output pixel (all stages of the chain).
+template <int C>
+__device__ __forceinline__ void feather_pixel(const StitchArgs& a, int frame, int x, int y, int feather_log2,
+                                              int (&v)[C]) {
+    const int F = 1 << feather_log2;
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = 0;
+    const int m = find_owner(a, x, y);
+    if (m < 0) return;
+    sample_layer<C>(a.L[m], frame, x, y, v);
+    for (int k = m + 1; k < a.n_layers; ++k) {
+        const McsLayer& in = a.L[k - 1].g;   // the rectangle pasted at stage k
+        const int d = min(min(x - in.rx0, in.rx1 - 1 - x), min(y - in.ry0, in.ry1 - 1 - y)) + 1;
+        if (d >= F) break;
+        int w[C];
+        if (sample_layer<C>(a.L[k], frame, x, y, w)) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = (d * v[c] + (F - d) * w[c] + (F >> 1)) >> feather_log2;
+        }
+    }
+}
+
+// Seam bands only: the feathered result differs from the overwrite result only within F pixels
+// inside the border of a pasted rectangle, so the regular (tiled) kernel composites the panorama
+// and this kernel then re-evaluates the band strips (plan->d_strips, at most four per stage) and
+// overwrites them.  One thread per band pixel; strips may overlap, the value does not depend on
+// the strip.
 template <int C>
 __global__ void __launch_bounds__(256)
-mcs_stitch_feather_kernel(const __grid_constant__ StitchArgs a, int feather_log2) {
-    const int x_first = blockIdx.x * MCS_TILE_W + threadIdx.x * 4;
-    const int y = blockIdx.y * MCS_TILE_H + threadIdx.y;
-    if (y >= a.out_h || x_first >= a.out_w) return;
+mcs_feather_band_kernel(const __grid_constant__ StitchArgs a, const int4* __restrict__ strips,
+                        const long long* __restrict__ prefix, int n_strips, int feather_log2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= prefix[n_strips]) return;
+    int s = 0;
+    while (s + 1 < n_strips && prefix[s + 1] <= i) ++s;
+    const int4 r = strips[s];
+    const int w = r.z - r.x;
+    const int j = (int)(i - prefix[s]);
+    const int y = r.y + j / w, x = r.x + j % w;
     const int frame = blockIdx.z;
-    const int F = 1 << feather_log2;
-    const int n_px = min(4, a.out_w - x_first);
-    uint8_t* out = a.dst + (long long)frame * a.dst_frame_stride + (long long)y * a.dst_pitch +
-                   (long long)x_first * C;
-    for (int i = 0; i < n_px; ++i) {
-        const int x = x_first + i;
-        int v[C];
+    int v[C];
+    feather_pixel<C>(a, frame, x, y, feather_log2, v);
+    uint8_t* out = a.dst + (long long)frame * a.dst_frame_stride + (long long)y * a.dst_pitch + (long long)x * C;
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = 0;
-        const int m = find_owner(a, x, y);
-        if (m >= 0) {
-            sample_layer<C>(a.L[m], frame, x, y, v);
-            for (int k = m + 1; k < a.n_layers; ++k) {
-                const McsLayer& in = a.L[k - 1].g;   // the rectangle pasted at stage k
-                const int d = min(min(x - in.rx0, in.rx1 - 1 - x), min(y - in.ry0, in.ry1 - 1 - y)) + 1;
-                if (d >= F) break;
-                int w[C];
-                if (sample_layer<C>(a.L[k], frame, x, y, w)) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) v[c] = (d * v[c] + (F - d) * w[c] + (F >> 1)) >> feather_log2;
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c) out[i * C + c] = (uint8_t)v[c];
-    }
+    for (int c = 0; c < C; ++c) out[c] = (uint8_t)v[c];
 }
 
 // --------------------------------------------------------------------------------------------
@@ -273,40 +285,39 @@ extern "C" int mcs_stitch_u8(const mcs_plan* plan_c, const uint8_t* const* src,
                       "mcs_stitch_u8: source %d pitch %lld < row bytes", k, (long long)src_pitch_bytes[k]);
     }
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (plan->feather_log2 > 0) {
-        StitchArgs fa;
-        fill_args(plan, fa, src, src_pitch_bytes, src_frame_stride, n_frames, dst, dst_pitch_bytes,
-                  dst_frame_stride);
-        dim3 block(MCS_TILE_W / 4, MCS_TILE_H, 1);
-        dim3 grid((plan->out_w + MCS_TILE_W - 1) / MCS_TILE_W, (plan->out_h + MCS_TILE_H - 1) / MCS_TILE_H, n_frames);
-        switch (plan->channels) {
-            case 1: mcs_stitch_feather_kernel<1><<<grid, block, 0, stream>>>(fa, plan->feather_log2); break;
-            case 3: mcs_stitch_feather_kernel<3><<<grid, block, 0, stream>>>(fa, plan->feather_log2); break;
-            default: mcs_stitch_feather_kernel<4><<<grid, block, 0, stream>>>(fa, plan->feather_log2); break;
-        }
-        mcs_count_launch(1);
-        MCS_CHECK_CUDA(cudaGetLastError());
-        plan->last_variant = 3;
-        return MCS_OK;
-    }
     const int force = plan->force_variant;
     const char* blocker = mcs_tiled_blocker(plan, src, src_pitch_bytes, src_frame_stride, n_frames, dst_pitch_bytes);
     if (force == 2 && blocker) {
         mcs_set_error("mcs_stitch_u8: tiled variant forced but unavailable: %s", blocker);
         return MCS_ERR_UNSUPPORTED;
     }
+    StitchArgs a;
     if (!blocker && force != 1) {
         int rc = mcs_launch_tiled(plan, src, src_pitch_bytes, src_frame_stride, n_frames, dst, dst_pitch_bytes,
                               dst_frame_stride, stream);
         if (rc != MCS_OK) return rc;
         plan->last_variant = 2;
-        return MCS_OK;
+    } else {
+        fill_args(plan, a, src, src_pitch_bytes, src_frame_stride, n_frames, dst, dst_pitch_bytes,
+                  dst_frame_stride);
+        MCS_CHECK_CUDA(launch_gather<false>(plan, a, nullptr, stream));
+        plan->last_variant = 1;
     }
-    StitchArgs a;
-    fill_args(plan, a, src, src_pitch_bytes, src_frame_stride, n_frames, dst, dst_pitch_bytes,
-              dst_frame_stride);
-    MCS_CHECK_CUDA(launch_gather<false>(plan, a, nullptr, stream));
-    plan->last_variant = 1;
+    if (plan->feather_log2 > 0 && plan->n_strips > 0) {
+        // feather blend: the pass above composited with the reference's overwrite; now the seam bands
+        fill_args(plan, a, src, src_pitch_bytes, src_frame_stride, n_frames, dst, dst_pitch_bytes,
+                  dst_frame_stride);
+        const long long total = plan->strip_pixels;
+        dim3 grid((unsigned)((total + 255) / 256), 1, n_frames);
+        switch (plan->channels) {
+            case 1: mcs_feather_band_kernel<1><<<grid, 256, 0, stream>>>(a, plan->d_strips, plan->d_strip_prefix, plan->n_strips, plan->feather_log2); break;
+            case 3: mcs_feather_band_kernel<3><<<grid, 256, 0, stream>>>(a, plan->d_strips, plan->d_strip_prefix, plan->n_strips, plan->feather_log2); break;
+            default: mcs_feather_band_kernel<4><<<grid, 256, 0, stream>>>(a, plan->d_strips, plan->d_strip_prefix, plan->n_strips, plan->feather_log2); break;
+        }
+        mcs_count_launch(1);
+        MCS_CHECK_CUDA(cudaGetLastError());
+        plan->last_variant = 3;
+    }
     return MCS_OK;
 }
 
