@@ -49,9 +49,8 @@ struct McsLayer {
     int reserved;
 };
 
-// Work item of the tiled kernel: the part of one 128 x 16 cell of a layer's own canvas grid that
-// the layer owns.  Cells are aligned to the layer frame (cell column 0 sits at canvas x = 128*i),
-// so a cell spans exactly two of OpenCV's 64-column coordinate blocks.
+// Work item of the tiled kernel: the part of one 128 x 16 cell that one layer owns.  Cells sit on
+// a grid anchored at panorama column 0 (cell column 0 at output x = 128*i).
 struct McsTile {
     int cx0;         // output x of cell column 0
     int y0;          // output y of the first row

@@ -1,11 +1,13 @@
 // Plan-time tiling for the tiled compositing kernel.
 //
 // The panorama is cut into work items ("tiles"), each owned by exactly one layer: layer k owns
-// rect_k minus rect_{k-1} (rectangles are nested, innermost first).  Tiles live on each layer's
-// own 128 x 16 cell grid, so a tile spans two whole 64-column coordinate blocks of OpenCV's
-// recipe.  A one-off kernel evaluates the exact fixed-point coordinates of every pixel of every
-// WARP tile and records the bounding box of the source pixels it touches; the host turns that
-// into the TMA box origin of the tile and the per-layer box size.
+// rect_k minus rect_{k-1} (rectangles are nested, innermost first).  Tiles live on one 128 x 16
+// cell grid anchored at panorama column 0 (a cell row is then a whole number of 32-byte sectors
+// of a 32-byte aligned panorama row).  One-off kernels evaluate OpenCV's exact fixed-point
+// coordinates of every pixel of every WARP tile: first the bounding box of the source pixels a
+// tile touches - the host turns that into the TMA box origin of the tile and the per-layer box
+// size - then one 32-bit sampling descriptor per pixel relative to that box.  The table is sorted
+// by class and carries a per-frame cost estimate for the launch-time work split.
 #include "mcs_device.cuh"
 
 #include <algorithm>
