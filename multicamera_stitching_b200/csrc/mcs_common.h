@@ -78,7 +78,7 @@ static_assert(sizeof(McsTile) == 32, "McsTile must stay 32 bytes");
 
 #define MCS_BOX_BYTES_MAX (40 * 1024)   // per staged source box
 
-#define MCS_FRAME_BLOCK_DEFAULT 32
+#define MCS_FRAME_BLOCK_DEFAULT 64
 #define MCS_SCHED_SLOTS 4
 #define MCS_SCHED_MAX_GRID 2047
 
