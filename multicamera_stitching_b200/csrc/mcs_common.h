@@ -65,8 +65,11 @@ struct McsTile {
 };
 static_assert(sizeof(McsTile) == 32, "McsTile must stay 32 bytes");
 
+#ifndef MCS_TILED_WARPS
+#define MCS_TILED_WARPS 8   // resampling warps of the tiled kernel; each owns two rows of a cell
+#endif
 #define MCS_CELL_W 128
-#define MCS_CELL_H 16
+#define MCS_CELL_H (2 * MCS_TILED_WARPS)
 
 #define MCS_TILE_ZERO 0   // nothing to sample: write zeros
 #define MCS_TILE_COPY 1   // verbatim paste of the source window

@@ -79,7 +79,7 @@ mcs_tile_bounds_kernel(const McsTile* __restrict__ tiles, const McsLayer* __rest
 //   bits 16..20  ax,  bits 21..25  ay   (1/32-px fractions)
 // sx / sy are clamped to [-2, src_w] / [-2, src_h] like in the bounds pass: at the clamp values
 // both taps of that axis read the zero fill of the box.  Slots the tile does not own get 0.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * MCS_TILED_WARPS)
 mcs_tile_desc_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restrict__ layers, int channels,
                      uint32_t* __restrict__ desc) {
     const int t = blockIdx.x;
@@ -89,7 +89,7 @@ mcs_tile_desc_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restri
     const double m0 = L.mi[0], m3 = L.mi[3], m6 = L.mi[6];
     const int sp = L.bw4 * 4;
     for (int j = 0; j < 8; ++j) {
-        const int row = warp + 8 * (j >> 2), col = lane + 32 * (j & 3);
+        const int row = warp + MCS_TILED_WARPS * (j >> 2), col = lane + 32 * (j & 3);
         uint32_t w = 0;
         if (col >= tile.c0 && col < tile.c1 && row < tile.h) {
             const int xl = tile.cx0 + col - L.ox, yl = tile.y0 + row - L.oy;
@@ -100,7 +100,7 @@ mcs_tile_desc_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restri
             const int b = (sy - tile.by) * sp + sx * channels - 4 * tile.bx;
             w = (uint32_t)b | ((uint32_t)(X & 31) << 16) | ((uint32_t)(Y & 31) << 21);
         }
-        desc[(size_t)t * (MCS_CELL_W * MCS_CELL_H) + (j * 8 + warp) * 32 + lane] = w;
+        desc[(size_t)t * (MCS_CELL_W * MCS_CELL_H) + (j * MCS_TILED_WARPS + warp) * 32 + lane] = w;
     }
 }
 
@@ -176,7 +176,7 @@ static int tile_cost(const McsTile& t) {
     int groups = 0;
     for (int g = 0; g < 4; ++g)
         if (32 * g < t.c1 && 32 * g + 32 > t.c0) ++groups;
-    const int px = groups * (t.h > 8 ? 2 : 1);     // pixels per thread of the busiest warp
+    const int px = groups * (t.h > MCS_TILED_WARPS ? 2 : 1);     // pixels per thread of the busiest warp
     return 63 + 26 * px;
 }
 
@@ -328,7 +328,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
     if (e == cudaSuccess && n_warp_tiles > 0) {
         e = cudaMalloc(&d_desc, sizeof(uint32_t) * MCS_CELL_W * MCS_CELL_H * (size_t)n_warp_tiles);
         if (e == cudaSuccess) {
-            mcs_tile_desc_kernel<<<n_warp_tiles, 256>>>(d_tiles, d_layers, C, d_desc);
+            mcs_tile_desc_kernel<<<n_warp_tiles, 32 * MCS_TILED_WARPS>>>(d_tiles, d_layers, C, d_desc);
             mcs_count_launch(1);
             e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
