@@ -143,6 +143,25 @@ const char* mcs_plan_tiled_status(const mcs_plan* plan);
  * tiled launch); the persistent grid is this times the SM count.  Diagnostics. */
 int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan);
 
+/*
+ * mcs_resize_linear_u8 - cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR) for
+ * n_frames uint8 images, bit-exact with OpenCV's 8-bit linear resize (11-bit coefficients,
+ * separable with the intermediate row rounding; exact 2 x 2 decimation takes OpenCV's area
+ * kernel, equal sizes copy).
+ *
+ * Replaces the shape fix-up of StitcherBase.stitch (StitcherClass.py:226-233: a frame whose
+ * shape differs from the calibrated BimgSize / AimgSize is resized before the warp; the
+ * MediaPlayer always takes this branch, MediaPlayer/view.py:408-409).
+ *
+ *   src, dst          device pointers to frame 0 (H x W x channels uint8, rows *_pitch_bytes
+ *                     apart, frames *_frame_stride bytes apart; strides ignored when n_frames == 1)
+ *   channels          1, 3 or 4
+ */
+int mcs_resize_linear_u8(const uint8_t* src, int src_w, int src_h, int64_t src_pitch_bytes,
+                         int64_t src_frame_stride, uint8_t* dst, int dst_w, int dst_h,
+                         int64_t dst_pitch_bytes, int64_t dst_frame_stride, int channels,
+                         int n_frames, void* cuda_stream);
+
 /* Number of kernels this library has launched in the calling process. */
 int64_t mcs_launch_count(void);
 

@@ -391,31 +391,102 @@ class StitcherBase(Debugger):
 
 
 # ---------------------------------------------------------------------------
+def _segments(stages, frame_shapes, debugger=None):
+    """Where the reference's shape fix-up (StitcherClass.py:226-233) strikes in this chain.
+
+    The reference checks, at every calibrated stage, imageB (the running canvas) against
+    ``BimgSize`` and imageA (the next camera) against ``AimgSize`` and resizes on any difference.
+    A camera frame - or the first image while it is still the raw camera 0 - can be resized
+    before the fused pass; a *composited* canvas of the wrong size cannot, so the chain is cut
+    there: the stages so far run as one plan, the canvas is resized, and the remaining stages run
+    as a second plan over it.  Returns a list of segments ``{a, b, base_hw, resize}``: stages
+    ``[a, b)``, the height / width the segment's first image is resized to (or None), and
+    ``{camera index: (h, w)}`` of the camera frames to resize."""
+    tail = tuple(frame_shapes[0][2:])
+    segs = []
+    cur = {"a": 0, "base_hw": None, "resize": {}, "n": 0}
+    cur_shape = tuple(frame_shapes[0])
+    for s, st in enumerate(stages):
+        if st.cachedAH is None:
+            continue
+        if cur_shape != tuple(st.BimgSize):
+            if debugger is not None:
+                debugger.debugger(DEBUG_LEVEL_0, "[STITCHER][{}] ImageB size should be {}, Image will be resized".format(
+                    st.sid, st.BimgSize), log_type="warn")
+            B = (int(st.BimgSize[0]), int(st.BimgSize[1]))
+            if cur_shape[:2] != B:
+                if cur["n"] == 0:
+                    cur["base_hw"] = B
+                else:
+                    cur["b"] = s
+                    segs.append(cur)
+                    cur = {"a": s, "base_hw": B, "resize": {}, "n": 0}
+        shapeA = tuple(frame_shapes[s + 1])
+        if shapeA != tuple(st.AimgSize):
+            if debugger is not None:
+                debugger.debugger(DEBUG_LEVEL_0, "[STITCHER][{}] ImageA size should be {}, Image will be resized".format(
+                    st.sid, st.AimgSize), log_type="warn")
+            A = (int(st.AimgSize[0]), int(st.AimgSize[1]))
+            if shapeA[:2] != A:
+                cur["resize"][s + 1] = A
+        cur["n"] += 1
+        cur_shape = tuple(st.result_shape()[:2]) + tail
+    cur["b"] = len(stages)
+    segs.append(cur)
+    return segs
+
+
 def _composite(engine, stages, frames, batched, out=None, debugger=None, feather_log2=0):
     """Run the fused kernel for this chain on these frames."""
     import torch  # local: keeps `import StitcherClass` cheap for calibration-only users
 
     on_device = _is_tensor(frames[0]) and frames[0].is_cuda
     shapes = [_shape_of(f)[1:] if batched else _shape_of(f) for f in frames]
-    device = frames[0].device if on_device else None
-    try:
-        plan = engine.plan_for(stages, shapes, device, feather_log2=feather_log2)
-    except PlanUnsupported as e:
-        if debugger is not None:
-            debugger.debugger(DEBUG_LEVEL_0, "[STITCHER] {}".format(e), log_type="err")
-        raise
-    if plan is None:
+    if all(st.cachedAH is None for st in stages):
         return frames[0]  # nothing calibrated: imageB passes through (reference :255-256)
-    if on_device:
-        n = int(frames[0].shape[0]) if batched else None
-        return plan.run(frames, out=out, n_frames=n)
-    if batched:
+    if batched and not on_device:
         raise TypeError("stitch_batch expects uint8 CUDA tensors")
-    with torch.cuda.device(plan.device):
-        dev = [None] * len(frames)
-        for l in plan.flat.layers:
-            dev[l.cam] = engine.upload(l.cam, frames[l.cam], plan.device)
-        res = plan.run(dev)
+    segs = _segments(stages, shapes, debugger)
+    device = frames[0].device if on_device else engine.device
+    n = int(frames[0].shape[0]) if batched else None
+
+    def plan_for(sub_stages, sub_shapes):
+        try:
+            return engine.plan_for(sub_stages, sub_shapes, device, feather_log2=feather_log2)
+        except PlanUnsupported as e:
+            if debugger is not None:
+                debugger.debugger(DEBUG_LEVEL_0, "[STITCHER] {}".format(e), log_type="err")
+            raise
+
+    with torch.cuda.device(device):
+        if len(segs) == 1 and segs[0]["base_hw"] is None and not segs[0]["resize"]:
+            # the regular case: every frame has its calibrated size, one launch
+            plan = plan_for(stages, shapes)
+            if on_device:
+                return plan.run(frames, out=out, n_frames=n)
+            dev = [None] * len(frames)
+            for l in plan.flat.layers:
+                dev[l.cam] = engine.upload(l.cam, frames[l.cam], device)
+            res = plan.run(dev)
+        else:
+            res = None
+            for i, seg in enumerate(segs):
+                a, b = seg["a"], seg["b"]
+                cams = [0 if res is None else None] + list(range(a + 1, b + 1))
+                sub = [res if c is None else (frames[c] if on_device else engine.upload(c, frames[c], device))
+                       for c in cams]
+                if seg["base_hw"] is not None:
+                    sub[0] = engine.resize(sub[0], seg["base_hw"], batched)
+                for c, hw in seg["resize"].items():
+                    sub[c - a] = engine.resize(sub[c - a], hw, batched)
+                sub_shapes = [_shape_of(t)[1:] if batched else _shape_of(t) for t in sub]
+                plan = plan_for(stages[a:b], sub_shapes)
+                if plan is None:
+                    res = sub[0]
+                else:
+                    res = plan.run(sub, out=out if i == len(segs) - 1 else None, n_frames=n)
+            if on_device:
+                return res
         host = torch.empty(res.shape, dtype=torch.uint8)
         host.copy_(res)  # synchronous D2H into a fresh array, like cv2 allocating its result
     return host.numpy()

@@ -24,7 +24,7 @@ EXPORTS = (
     "mcs_plan_owned_pixels", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_last_variant",
     "mcs_plan_force_variant",
     "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_launch_count",
-    "mcs_match_hamming_top2", "mcs_ransac_homography",
+    "mcs_match_hamming_top2", "mcs_ransac_homography", "mcs_resize_linear_u8",
 )
 
 
@@ -89,6 +89,10 @@ def load(build_if_missing=False):
     lib.mcs_ransac_homography.restype = ctypes.c_int
     lib.mcs_ransac_homography.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_float,
                                           _vp, _vp, _vp, _vp, ctypes.c_int, _vp]
+    lib.mcs_resize_linear_u8.restype = ctypes.c_int
+    lib.mcs_resize_linear_u8.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                         _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                         ctypes.c_int, ctypes.c_int, _vp]
     _lib = lib
     return lib
 
@@ -101,6 +105,15 @@ def check(rc, what):
 
 def launch_count():
     return int(load().mcs_launch_count())
+
+
+def resize_linear_u8(src_ptr, src_w, src_h, src_pitch, src_frame_stride, dst_ptr, dst_w, dst_h, dst_pitch,
+                     dst_frame_stride, channels, n_frames, stream=0):
+    """``cv2.resize(..., INTER_LINEAR)`` of ``n_frames`` uint8 device images (include/mcs.h)."""
+    check(load().mcs_resize_linear_u8(_vp(int(src_ptr)), int(src_w), int(src_h), int(src_pitch),
+                                      int(src_frame_stride), _vp(int(dst_ptr)), int(dst_w), int(dst_h),
+                                      int(dst_pitch), int(dst_frame_stride), int(channels), int(n_frames),
+                                      _vp(int(stream))), "mcs_resize_linear_u8")
 
 
 def _i32(a):

@@ -1,0 +1,136 @@
+// Shape fix-up of the compositing path: cv2.resize(img, (W, H), interpolation=INTER_LINEAR) for
+// uint8 frames (StitcherClass.py:226-233), bit-exact with OpenCV's 8-bit linear resize.
+//
+// Recipe (OpenCV resize.cpp, restated in oracle/resize_model.py):
+//   scale = 1 / (n_dst / n_src)                                     -- float64, computed on the host
+//   f = float32((d + 0.5) * scale - 0.5); s = floor(f); f -= s      -- float32 after the cast
+//   columns only: s < 0 -> (0, f = 0);  s >= n_src - 1 -> (n_src - 1, f = 0)
+//   w0 = rint(float32(1 - f) * 2048), w1 = rint(f * 2048)
+//   rows: taps clip(s, 0, n_src - 1) and clip(s + 1, 0, n_src - 1), weights as computed
+//   h_r = p[r][sx] * a0 + p[r][sx + 1] * a1
+//   out = (((b0 * (h_0 >> 4)) >> 16) + ((b1 * (h_1 >> 4)) >> 16) + 2) >> 2
+//   exact 2 x 2 decimation goes through OpenCV's area kernel: (p00 + p01 + p10 + p11 + 2) >> 2
+// The float operations use the round-to-nearest intrinsics, which are never contracted.
+#include "mcs_common.h"
+
+struct ResizeArgs {
+    const uint8_t* src;
+    uint8_t* dst;
+    long long src_pitch, src_frame_stride, dst_pitch, dst_frame_stride;
+    double scale_x, scale_y;
+    int src_w, src_h, dst_w, dst_h;
+    int area2;   // exact 2 x 2 decimation
+};
+
+__device__ __forceinline__ void linear_coef(int d, double scale, int n_src, bool clamp_edges, int& s, int& w0,
+                                            int& w1) {
+    float f = __double2float_rn(__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5));
+    s = __float2int_rd(f);
+    f = __fsub_rn(f, (float)s);
+    if (clamp_edges) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
+    }
+    w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+// One thread per 4 consecutive output pixels of one row (block 32 x 8: a warp writes 128 pixels of
+// a row), frames along grid z.  Taps come straight from global memory through L1.
+template <int C>
+__global__ void __launch_bounds__(256)
+mcs_resize_linear_kernel(const __grid_constant__ ResizeArgs a) {
+    const int x_first = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (y >= a.dst_h || x_first >= a.dst_w) return;
+    const uint8_t* src = a.src + (long long)blockIdx.z * a.src_frame_stride;
+    const int n_px = min(4, a.dst_w - x_first);
+    uint8_t px[4 * C];
+
+    if (a.area2) {
+        const uint8_t* r0 = src + (long long)(2 * y) * a.src_pitch;
+        const uint8_t* r1 = r0 + a.src_pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < n_px) {
+                const int o = 2 * (x_first + i) * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    px[i * C + c] = (uint8_t)((__ldg(r0 + o + c) + __ldg(r0 + o + C + c) + __ldg(r1 + o + c) +
+                                               __ldg(r1 + o + C + c) + 2) >> 2);
+            }
+        }
+    } else {
+        int sy, b0, b1;
+        linear_coef(y, a.scale_y, a.src_h, false, sy, b0, b1);
+        const uint8_t* r0 = src + (long long)max(0, min(a.src_h - 1, sy)) * a.src_pitch;
+        const uint8_t* r1 = src + (long long)max(0, min(a.src_h - 1, sy + 1)) * a.src_pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < n_px) {
+                int sx, a0, a1;
+                linear_coef(x_first + i, a.scale_x, a.src_w, true, sx, a0, a1);
+                const int o0 = sx * C, o1 = min(sx + 1, a.src_w - 1) * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int h0 = __ldg(r0 + o0 + c) * a0 + __ldg(r0 + o1 + c) * a1;
+                    const int h1 = __ldg(r1 + o0 + c) * a0 + __ldg(r1 + o1 + c) * a1;
+                    px[i * C + c] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+                }
+            }
+        }
+    }
+
+    uint8_t* out = a.dst + (long long)blockIdx.z * a.dst_frame_stride + (long long)y * a.dst_pitch +
+                   (long long)x_first * C;
+    if (n_px == 4 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+        for (int wd = 0; wd < C; ++wd)
+            o32[wd] = (uint32_t)px[4 * wd] | ((uint32_t)px[4 * wd + 1] << 8) | ((uint32_t)px[4 * wd + 2] << 16) |
+                      ((uint32_t)px[4 * wd + 3] << 24);
+    } else {
+        for (int b = 0; b < n_px * C; ++b) out[b] = px[b];
+    }
+}
+
+extern "C" int mcs_resize_linear_u8(const uint8_t* src, int src_w, int src_h, int64_t src_pitch_bytes,
+                                    int64_t src_frame_stride, uint8_t* dst, int dst_w, int dst_h,
+                                    int64_t dst_pitch_bytes, int64_t dst_frame_stride, int channels,
+                                    int n_frames, void* cuda_stream) {
+    MCS_CHECK_ARG(channels == 1 || channels == 3 || channels == 4,
+                  "mcs_resize_linear_u8: channels=%d (supported: 1, 3, 4)", channels);
+    MCS_CHECK_ARG(n_frames >= 0 && n_frames <= 65535, "mcs_resize_linear_u8: n_frames=%d outside 0..65535", n_frames);
+    MCS_CHECK_ARG(src_w > 0 && src_h > 0 && src_w < (1 << 24) && src_h < (1 << 24),
+                  "mcs_resize_linear_u8: source size %dx%d out of range", src_w, src_h);
+    MCS_CHECK_ARG(dst_w >= 0 && dst_h >= 0 && dst_w < (1 << 24) && dst_h < (1 << 24),
+                  "mcs_resize_linear_u8: destination size %dx%d out of range", dst_w, dst_h);
+    if (n_frames == 0 || dst_w == 0 || dst_h == 0) return MCS_OK;
+    MCS_CHECK_ARG(src != nullptr && dst != nullptr, "mcs_resize_linear_u8: NULL image pointer");
+    MCS_CHECK_ARG(src_pitch_bytes >= (int64_t)src_w * channels && dst_pitch_bytes >= (int64_t)dst_w * channels,
+                  "mcs_resize_linear_u8: pitch smaller than a row");
+    ResizeArgs a;
+    a.src = src;
+    a.dst = dst;
+    a.src_pitch = src_pitch_bytes;
+    a.src_frame_stride = n_frames > 1 ? src_frame_stride : 0;
+    a.dst_pitch = dst_pitch_bytes;
+    a.dst_frame_stride = n_frames > 1 ? dst_frame_stride : 0;
+    // cv::resize: inv_scale = (double)dsize / ssize, then scale = 1. / inv_scale
+    volatile double inv_x = (double)dst_w / (double)src_w, inv_y = (double)dst_h / (double)src_h;
+    a.scale_x = 1.0 / inv_x;
+    a.scale_y = 1.0 / inv_y;
+    a.src_w = src_w; a.src_h = src_h; a.dst_w = dst_w; a.dst_h = dst_h;
+    a.area2 = (a.scale_x == 2.0 && a.scale_y == 2.0) ? 1 : 0;
+    const dim3 block(32, 8, 1);
+    const dim3 grid((dst_w + 127) / 128, (dst_h + 7) / 8, n_frames);
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    switch (channels) {
+        case 1: mcs_resize_linear_kernel<1><<<grid, block, 0, stream>>>(a); break;
+        case 3: mcs_resize_linear_kernel<3><<<grid, block, 0, stream>>>(a); break;
+        default: mcs_resize_linear_kernel<4><<<grid, block, 0, stream>>>(a); break;
+    }
+    mcs_count_launch(1);
+    MCS_CHECK_CUDA(cudaGetLastError());
+    return MCS_OK;
+}

@@ -156,6 +156,31 @@ class CompositeEngine(object):
         buf.copy_(t, non_blocking=True)
         return buf
 
+    def resize(self, t, hw, batched=False):
+        """``cv2.resize(frame, (w, h), interpolation=cv2.INTER_LINEAR)`` of a uint8 CUDA tensor
+        ([H,W[,C]] or, batched, [F,H,W[,C]]) into a new tensor: the shape fix-up of the
+        reference's stitch (StitcherClass.py:226-233) through ``mcs_resize_linear_u8``."""
+        if t.dtype != torch.uint8 or not t.is_cuda:
+            raise TypeError("resize expects a uint8 CUDA tensor, got %s on %s" % (t.dtype, t.device))
+        lead = 1 if batched else 0
+        if t.dim() - lead not in (2, 3):
+            raise ValueError("resize expects H x W or H x W x C frames, got shape %r" % (tuple(t.shape),))
+        C = int(t.shape[lead + 2]) if t.dim() - lead == 3 else 1
+        F = int(t.shape[0]) if batched else 1
+        hs, ws = int(t.shape[lead]), int(t.shape[lead + 1])
+        hd, wd = int(hw[0]), int(hw[1])
+        st = t.stride()
+        dense = st[-1] == 1 and (t.dim() - lead == 2 or st[-2] == C)
+        if not dense or (batched and F > 1 and st[0] < 0):
+            t = t.contiguous()
+            st = t.stride()
+        out = torch.empty(t.shape[:lead] + (hd, wd) + t.shape[lead + 2:], dtype=torch.uint8, device=t.device)
+        with torch.cuda.device(t.device):
+            _cabi.resize_linear_u8(t.data_ptr(), ws, hs, st[lead], st[0] if batched else 0,
+                                   out.data_ptr(), wd, hd, wd * C, hd * wd * C, C, F,
+                                   torch.cuda.current_stream().cuda_stream)
+        return out
+
     def reset(self):
         self._plans.clear()
         self._staging.clear()

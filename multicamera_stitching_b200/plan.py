@@ -74,11 +74,17 @@ def flatten_chain(stages, cam_shapes):
             continue  # uncalibrated stage: the running canvas passes through
         any_calibrated = True
         shapeA = tuple(int(v) for v in cam_shapes[s + 1])
-        if cur_shape != tuple(_field(st, "BimgSize")):
+        # Only the geometry has to agree here.  The reference compares whole shape tuples and
+        # resizes on any difference (StitcherClass.py:226-233); a frame that differs from the
+        # calibrated one in its channel layout only is "resized" to its own size, i.e. unchanged.
+        # Frames of another height / width are resized by the caller before planning
+        # (StitcherClass._composite), which also splits the chain where a composited canvas
+        # would have to be resized.
+        if cur_shape[:2] != tuple(_field(st, "BimgSize"))[:2]:
             raise PlanUnsupported(
                 "stage %d: running canvas has shape %r but was calibrated for %r (resizing a "
                 "composited canvas is not expressible in one pass)" % (s, cur_shape, tuple(_field(st, "BimgSize"))))
-        if shapeA != tuple(_field(st, "AimgSize")):
+        if shapeA[:2] != tuple(_field(st, "AimgSize"))[:2]:
             raise PlanUnsupported("stage %d: frame shape %r != calibrated %r"
                                   % (s, shapeA, tuple(_field(st, "AimgSize"))))
         if shapeA[2:] != tail:
