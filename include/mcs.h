@@ -38,6 +38,7 @@ extern "C" {
 /* layer kinds */
 #define MCS_LAYER_COPY       0   /* verbatim paste  (camera 0 / image B)      */
 #define MCS_LAYER_WARP       1   /* cv2.warpPerspective(INTER_LINEAR) resample */
+#define MCS_LAYER_REMAP      2   /* cv2.remap(INTER_LINEAR) through a fixed-point map */
 
 typedef struct mcs_plan mcs_plan;
 
@@ -60,7 +61,7 @@ const char* mcs_last_error(void);
  *
  *   n_layers   1..MCS_MAX_LAYERS
  *   channels   1, 3 or 4 (bytes per pixel of every source and of the output)
- *   layer_kind [n]    MCS_LAYER_COPY | MCS_LAYER_WARP
+ *   layer_kind [n]    MCS_LAYER_COPY | MCS_LAYER_WARP (MCS_LAYER_REMAP: mcs_plan_create_maps)
  *   src_hw     [n*2]  source frame (height, width) of each layer
  *   fwd_h      [n*9]  row-major float64 FORWARD homography of each WARP layer,
  *                     exactly the `M` the reference hands to
@@ -79,6 +80,35 @@ int mcs_plan_create(mcs_plan** out, int n_layers, int channels,
                     const int32_t* layer_kind, const int32_t* src_hw,
                     const double* fwd_h, const int32_t* origin_xy,
                     const int32_t* rect_xyxy, int out_w, int out_h);
+
+/*
+ * mcs_plan_create_maps - mcs_plan_create with MCS_LAYER_REMAP layers: the source coordinates
+ * of such a layer come from a fixed-point map pair in OpenCV's own format instead of a
+ * homography, and the layer is resampled exactly like cv2.remap(src, map_xy, map_frac,
+ * INTER_LINEAR) with BORDER_CONSTANT 0.
+ *
+ * Replaces, for the per-camera pre-warp in front of the stitcher, cv2.undistort(src,
+ * cameraMatrix, distCoeffs) (video_mapping_node.py:155-158, MediaPlayer/view.py:378-381,
+ * Intrinsic.py:234-235; cv::undistort is initUndistortRectifyMap(CV_16SC2) + remap, and
+ * Intrinsic.py:238-240 spells that form out).  The maps are calibration outputs, computed once
+ * on the host; the per-frame resampling is the kernel's.
+ *
+ *   map_xy    host array [n_layers] of HOST pointers; for a REMAP layer k: map_hw[2k] rows x
+ *             map_hw[2k+1] columns x 2 int16 (x, y) = integer source coordinates of every pixel
+ *             of the layer's own canvas frame (CV_16SC2); NULL entries for other layers
+ *   map_frac  the same for the uint16 interpolation-table index ((fy << 5) | fx, CV_16UC1);
+ *             a NULL entry means all zero
+ *   map_hw    host int32 [n_layers*2]
+ * The maps are copied; the caller may free them when the call returns.  src_hw of a REMAP layer
+ * is the size of the source image, the map size that of its output.  With all three NULL this is
+ * mcs_plan_create.
+ */
+int mcs_plan_create_maps(mcs_plan** out, int n_layers, int channels,
+                         const int32_t* layer_kind, const int32_t* src_hw,
+                         const double* fwd_h, const int32_t* origin_xy,
+                         const int32_t* rect_xyxy, int out_w, int out_h,
+                         const int16_t* const* map_xy, const uint16_t* const* map_frac,
+                         const int32_t* map_hw);
 
 int mcs_plan_destroy(mcs_plan* plan);
 

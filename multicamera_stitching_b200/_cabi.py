@@ -16,11 +16,12 @@ MCS_OK = 0
 MCS_MAX_LAYERS = 16
 MCS_LAYER_COPY = 0
 MCS_LAYER_WARP = 1
+MCS_LAYER_REMAP = 2
 ABI_VERSION = 1
 
 # every symbol include/mcs.h declares
 EXPORTS = (
-    "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_destroy",
+    "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_create_maps", "mcs_plan_destroy",
     "mcs_plan_owned_pixels", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_last_variant",
     "mcs_plan_force_variant",
     "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_launch_count",
@@ -64,6 +65,10 @@ def load(build_if_missing=False):
     lib.mcs_plan_create.restype = ctypes.c_int
     lib.mcs_plan_create.argtypes = [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _c_i32p, _c_i32p,
                                     _c_f64p, _c_i32p, _c_i32p, ctypes.c_int, ctypes.c_int]
+    lib.mcs_plan_create_maps.restype = ctypes.c_int
+    lib.mcs_plan_create_maps.argtypes = [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _c_i32p, _c_i32p,
+                                         _c_f64p, _c_i32p, _c_i32p, ctypes.c_int, ctypes.c_int,
+                                         ctypes.POINTER(_vp), ctypes.POINTER(_vp), _c_i32p]
     lib.mcs_plan_destroy.restype = ctypes.c_int
     lib.mcs_plan_destroy.argtypes = [_vp]
     lib.mcs_plan_owned_pixels.restype = ctypes.c_int
@@ -124,7 +129,9 @@ def _i32(a):
 class Plan(object):
     """Owning wrapper of an ``mcs_plan*``."""
 
-    def __init__(self, layer_kind, src_hw, fwd_h, origin_xy, rect_xyxy, out_w, out_h, channels):
+    def __init__(self, layer_kind, src_hw, fwd_h, origin_xy, rect_xyxy, out_w, out_h, channels, maps=None):
+        """``maps``: optional list, one entry per layer: ``None`` or the ``(xy, frac)`` fixed-point
+        map pair of a REMAP layer (int16 H x W x 2, uint16 H x W or None)."""
         lib = load()
         n = len(layer_kind)
         kind, kind_p = _i32(layer_kind)
@@ -133,9 +140,34 @@ class Plan(object):
         rect, rect_p = _i32(np.reshape(rect_xyxy, (n, 4)))
         h = np.ascontiguousarray(np.reshape(fwd_h, (n, 9)), dtype=np.float64)
         handle = _vp()
-        check(lib.mcs_plan_create(ctypes.byref(handle), n, int(channels), kind_p, hw_p,
-                                  h.ctypes.data_as(_c_f64p), org_p, rect_p, int(out_w), int(out_h)),
-              "mcs_plan_create")
+        if maps is None or all(m is None for m in maps):
+            check(lib.mcs_plan_create(ctypes.byref(handle), n, int(channels), kind_p, hw_p,
+                                      h.ctypes.data_as(_c_f64p), org_p, rect_p, int(out_w), int(out_h)),
+                  "mcs_plan_create")
+        else:
+            keep = []   # host arrays must outlive the call
+            xy_p = (_vp * n)()
+            fr_p = (_vp * n)()
+            mhw = np.zeros((n, 2), dtype=np.int32)
+            for k, m in enumerate(maps):
+                if m is None:
+                    continue
+                xy = np.ascontiguousarray(m[0], dtype=np.int16)
+                if xy.ndim != 3 or xy.shape[2] != 2:
+                    raise ValueError("layer %d: map_xy must be H x W x 2 int16, got %r" % (k, xy.shape))
+                keep.append(xy)
+                xy_p[k] = xy.ctypes.data
+                mhw[k] = xy.shape[:2]
+                if m[1] is not None:
+                    fr = np.ascontiguousarray(m[1], dtype=np.uint16)
+                    if fr.shape != xy.shape[:2]:
+                        raise ValueError("layer %d: map_frac shape %r != %r" % (k, fr.shape, xy.shape[:2]))
+                    keep.append(fr)
+                    fr_p[k] = fr.ctypes.data
+            check(lib.mcs_plan_create_maps(ctypes.byref(handle), n, int(channels), kind_p, hw_p,
+                                           h.ctypes.data_as(_c_f64p), org_p, rect_p, int(out_w), int(out_h),
+                                           xy_p, fr_p, mhw.ctypes.data_as(_c_i32p)),
+                  "mcs_plan_create_maps")
         self._h = handle
         self.n_layers = n
         self.channels = int(channels)

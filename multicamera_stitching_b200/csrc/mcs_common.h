@@ -46,7 +46,8 @@ struct McsLayer {
     int bh;                  // tiled variant: staged box height in rows (<= 256)
     int w_safe;              // |W| stays in [1e-3, 1e6] with one sign over the rectangle: the
                              // branch-free division of the tiled kernel is exact there
-    int reserved;
+    int map_w, map_h;        // REMAP layers: size of the coordinate map (= the layer's canvas frame)
+    const int2* map;         // REMAP layers: device, map_h x map_w 1/32-px source coordinates (X, Y)
 };
 
 // Work item of the tiled kernel: the part of one 128 x 16 cell that one layer owns.  Cells sit on
@@ -105,6 +106,7 @@ struct mcs_plan {
     int box_bytes;           // shared-memory bytes of one staging buffer (max over layers, 128-aligned)
     McsTile* d_tiles;
     McsLayer* d_layers;
+    int2* d_maps[MCS_MAX_LAYERS];   // coordinate maps of the REMAP layers (owned by the plan)
     uint32_t* d_desc;        // per-pixel descriptors of the WARP tiles, 2048 words per tile (mcs_tiles.cu)
     int frame_block;         // frames per sweep of the tile table (mcs_launch_tiled)
     // cache of the TMA descriptors of the last call (keyed by the source table)

@@ -39,3 +39,21 @@ __device__ __forceinline__ void fixed_coords(double m0, double m3, double m6, co
 
 // saturate_cast<short> of the integer part of a 1/32-px coordinate
 __device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
+
+// 1/32-px source coordinates of pixel (xl, yl) of a layer's own canvas frame: the homography
+// recipe above for WARP layers, the plan's fixed-point map (cv2.remap with CV_16SC2 + CV_16UC1
+// maps: X = 32 * map_x + fx, Y = 32 * map_y + fy) for REMAP layers.
+__device__ __forceinline__ void layer_coords(const McsLayer& L, int xl, int yl, int& X, int& Y) {
+    if (L.kind == MCS_LAYER_REMAP) {
+        if ((unsigned)xl < (unsigned)L.map_w && (unsigned)yl < (unsigned)L.map_h) {
+            const int2 m = __ldg(L.map + (size_t)yl * L.map_w + xl);
+            X = m.x;
+            Y = m.y;
+        } else {
+            X = Y = -64 * 32;   // outside the map: no tap inside any source
+        }
+        return;
+    }
+    const RowBlock rb = row_block(L.mi, xl & ~63, yl);
+    fixed_coords(L.mi[0], L.mi[3], L.mi[6], rb, xl & 63, X, Y);
+}

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <new>
 #include <string.h>
+#include <vector>
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -47,10 +48,45 @@ bool mcs_invert3x3(const double* s, double* t) {
     return true;
 }
 
+static void free_maps(mcs_plan* p) {
+    for (int k = 0; k < MCS_MAX_LAYERS; ++k) {
+        if (p->d_maps[k]) cudaFree(p->d_maps[k]);
+        p->d_maps[k] = nullptr;
+    }
+}
+
+// Uploads the fixed-point map of REMAP layer k in the packed form the kernels read:
+// (X, Y) = (32 * map_x + fx, 32 * map_y + fy) with fx = frac & 31, fy = (frac >> 5) & 31, which is
+// how cv::remap splits a CV_16SC2 + CV_16UC1 map pair (INTER_BITS = 5).
+static int upload_map(mcs_plan* p, int k, const int16_t* xy, const uint16_t* frac, int rows, int cols) {
+    const size_t n = (size_t)rows * cols;
+    std::vector<int2> packed(n);
+    for (size_t i = 0; i < n; ++i) {
+        const int f = frac ? frac[i] : 0;
+        packed[i] = make_int2((int)xy[2 * i] * 32 + (f & 31), (int)xy[2 * i + 1] * 32 + ((f >> 5) & 31));
+    }
+    MCS_CHECK_CUDA(cudaMalloc(&p->d_maps[k], sizeof(int2) * n));
+    MCS_CHECK_CUDA(cudaMemcpy(p->d_maps[k], packed.data(), sizeof(int2) * n, cudaMemcpyHostToDevice));
+    p->layers[k].map = p->d_maps[k];
+    p->layers[k].map_w = cols;
+    p->layers[k].map_h = rows;
+    return MCS_OK;
+}
+
 extern "C" int mcs_plan_create(mcs_plan** out, int n_layers, int channels,
                                const int32_t* layer_kind, const int32_t* src_hw,
                                const double* fwd_h, const int32_t* origin_xy,
                                const int32_t* rect_xyxy, int out_w, int out_h) {
+    return mcs_plan_create_maps(out, n_layers, channels, layer_kind, src_hw, fwd_h, origin_xy, rect_xyxy, out_w,
+                                out_h, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mcs_plan_create_maps(mcs_plan** out, int n_layers, int channels,
+                                    const int32_t* layer_kind, const int32_t* src_hw,
+                                    const double* fwd_h, const int32_t* origin_xy,
+                                    const int32_t* rect_xyxy, int out_w, int out_h,
+                                    const int16_t* const* map_xy, const uint16_t* const* map_frac,
+                                    const int32_t* map_hw) {
     MCS_CHECK_ARG(out != nullptr, "mcs_plan_create: out is NULL");
     *out = nullptr;
     MCS_CHECK_ARG(n_layers >= 1 && n_layers <= MCS_MAX_LAYERS,
@@ -96,7 +132,7 @@ extern "C" int mcs_plan_create(mcs_plan** out, int n_layers, int channels,
         if (x1 < x0) x1 = x0;
         if (y1 < y0) y1 = y0;
         L.rx0 = x0; L.ry0 = y0; L.rx1 = x1; L.ry1 = y1;
-        bool ok = (L.kind == MCS_LAYER_COPY || L.kind == MCS_LAYER_WARP) && L.src_h > 0 &&
+        bool ok = (L.kind == MCS_LAYER_COPY || L.kind == MCS_LAYER_WARP || L.kind == MCS_LAYER_REMAP) && L.src_h > 0 &&
                   L.src_w > 0 && L.src_h < 32767 && L.src_w < 32767;  // cv2.remap's short-coordinate limit
         // canvas-frame coordinates (x - ox, y - oy) must be non-negative inside the rectangle:
         // the 64-column block split of the coordinate recipe is defined on x >= 0.
@@ -109,12 +145,38 @@ extern "C" int mcs_plan_create(mcs_plan** out, int n_layers, int channels,
         if (!ok) {
             mcs_set_error("mcs_plan_create: layer %d invalid (kind=%d src=%dx%d origin=(%d,%d) "
                           "rect=[%d,%d,%d,%d))", k, L.kind, L.src_w, L.src_h, L.ox, L.oy, x0, y0, x1, y1);
+            free_maps(p);
             delete p;
             return MCS_ERR_INVALID;
         }
-        if (L.kind == MCS_LAYER_WARP) {
+        if (L.kind == MCS_LAYER_REMAP) {
+            const int rows = map_hw ? map_hw[2 * k] : 0, cols = map_hw ? map_hw[2 * k + 1] : 0;
+            if (!map_xy || !map_xy[k] || rows <= 0 || cols <= 0 || rows >= (1 << 15) || cols >= (1 << 15)) {
+                mcs_set_error("mcs_plan_create_maps: layer %d is a REMAP layer without a valid map (%d x %d)", k,
+                              rows, cols);
+                free_maps(p);
+                delete p;
+                return MCS_ERR_INVALID;
+            }
+            // the map must cover the visible rectangle (in the layer's own canvas frame)
+            if (x1 > x0 && y1 > y0 && (x1 - L.ox > cols || y1 - L.oy > rows)) {
+                mcs_set_error("mcs_plan_create_maps: layer %d: rectangle [%d,%d,%d,%d) exceeds its %d x %d map at "
+                              "origin (%d,%d)", k, x0, y0, x1, y1, cols, rows, L.ox, L.oy);
+                free_maps(p);
+                delete p;
+                return MCS_ERR_INVALID;
+            }
+            const int rc = upload_map(p, k, map_xy[k], map_frac ? map_frac[k] : nullptr, rows, cols);
+            if (rc != MCS_OK) {
+                free_maps(p);
+                delete p;
+                return rc;
+            }
+            L.mi[0] = L.mi[4] = L.mi[8] = 1.0;
+        } else if (L.kind == MCS_LAYER_WARP) {
             if (!fwd_h) {
                 mcs_set_error("mcs_plan_create: fwd_h is NULL but layer %d is a WARP layer", k);
+                free_maps(p);
                 delete p;
                 return MCS_ERR_INVALID;
             }
@@ -148,6 +210,7 @@ extern "C" int mcs_plan_destroy(mcs_plan* plan) {
     if (plan->d_strips) cudaFree(plan->d_strips);
     if (plan->d_strip_prefix) cudaFree(plan->d_strip_prefix);
     mcs_plan_free_tiles(plan);
+    free_maps(plan);
     delete plan;
     return MCS_OK;
 }

@@ -116,14 +116,18 @@ mcs_stitch_gather_kernel(const __grid_constant__ StitchArgs a, unsigned long lon
                 if (L.g.kind == MCS_LAYER_COPY) {
                     if (!STATS) load_px<C>(src + (long long)yl * L.pitch + (long long)xl * C, v);
                 } else {
-                    const int xb = xl & ~63;
-                    if (k != prev_owner || xb != prev_xb) {
-                        rb = row_block(L.g.mi, xb, yl);
-                        prev_owner = k;
-                        prev_xb = xb;
-                    }
                     int X, Y;
-                    fixed_coords(L.g.mi[0], L.g.mi[3], L.g.mi[6], rb, xl & 63, X, Y);
+                    if (L.g.kind == MCS_LAYER_REMAP) {
+                        layer_coords(L.g, xl, yl, X, Y);
+                    } else {
+                        const int xb = xl & ~63;
+                        if (k != prev_owner || xb != prev_xb) {
+                            rb = row_block(L.g.mi, xb, yl);
+                            prev_owner = k;
+                            prev_xb = xb;
+                        }
+                        fixed_coords(L.g.mi[0], L.g.mi[3], L.g.mi[6], rb, xl & 63, X, Y);
+                    }
                     if (STATS) {
                         const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
                         touched = ((unsigned)sx < (unsigned)L.g.src_w || (unsigned)(sx + 1) < (unsigned)L.g.src_w) &&
@@ -177,9 +181,8 @@ __device__ __forceinline__ bool sample_layer(const LayerArgs& L, int frame, int 
         load_px<C>(src + (long long)yl * L.pitch + (long long)xl * C, v);
         return true;
     }
-    const RowBlock rb = row_block(L.g.mi, xl & ~63, yl);
     int X, Y;
-    fixed_coords(L.g.mi[0], L.g.mi[3], L.g.mi[6], rb, xl & 63, X, Y);
+    layer_coords(L.g, xl, yl, X, Y);
     return sample_u8<C>(src, L.pitch, L.g.src_w, L.g.src_h, X, Y, v);
 }
 

@@ -35,15 +35,13 @@ mcs_tile_bounds_kernel(const McsTile* __restrict__ tiles, const McsLayer* __rest
     int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN, touched = 0, clamped = 0;
     if (tile.layer >= 0 && tile.cls == MCS_TILE_WARP) {
         const McsLayer& L = layers[tile.layer];
-        const double m0 = L.mi[0], m3 = L.mi[3], m6 = L.mi[6];
         const int w = tile.c1 - tile.c0;
         const int n = w * tile.h;
         for (int i = lane; i < n; i += 32) {
             const int r = i / w, c = tile.c0 + (i - r * w);
             const int xl = tile.cx0 + c - L.ox, yl = tile.y0 + r - L.oy;
-            const RowBlock rb = row_block(L.mi, xl & ~63, yl);
             int X, Y;
-            fixed_coords(m0, m3, m6, rb, xl & 63, X, Y);
+            layer_coords(L, xl, yl, X, Y);
             const int rsx = sat16(X >> 5), rsy = sat16(Y >> 5);
             const bool in = ((unsigned)rsx < (unsigned)L.src_w || (unsigned)(rsx + 1) < (unsigned)L.src_w) &&
                             ((unsigned)rsy < (unsigned)L.src_h || (unsigned)(rsy + 1) < (unsigned)L.src_h);
@@ -86,16 +84,14 @@ mcs_tile_desc_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const McsTile tile = tiles[t];
     const McsLayer& L = layers[tile.layer];
-    const double m0 = L.mi[0], m3 = L.mi[3], m6 = L.mi[6];
     const int sp = L.bw4 * 4;
     for (int j = 0; j < 8; ++j) {
         const int row = warp + MCS_TILED_WARPS * (j >> 2), col = lane + 32 * (j & 3);
         uint32_t w = 0;
         if (col >= tile.c0 && col < tile.c1 && row < tile.h) {
             const int xl = tile.cx0 + col - L.ox, yl = tile.y0 + row - L.oy;
-            const RowBlock rb = row_block(L.mi, xl & ~63, yl);
             int X, Y;
-            fixed_coords(m0, m3, m6, rb, xl & 63, X, Y);
+            layer_coords(L, xl, yl, X, Y);
             const int sx = max(-2, min(L.src_w, sat16(X >> 5))), sy = max(-2, min(L.src_h, sat16(Y >> 5)));
             const int b = (sy - tile.by) * sp + sx * channels - 4 * tile.bx;
             w = (uint32_t)b | ((uint32_t)(X & 31) << 16) | ((uint32_t)(Y & 31) << 21);

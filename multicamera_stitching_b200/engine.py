@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .plan import PlanUnsupported, flatten_chain, plan_tables, stage_signature
+from .plan import PlanUnsupported, flatten_chain, plan_maps, plan_tables, stage_signature
 
 
 def _stage_field(st, name):
@@ -29,7 +29,8 @@ class CompiledPlan(object):
         self.feather_log2 = int(feather_log2)
         with torch.cuda.device(self.device):
             kind, src_hw, fwd, origin, rect = plan_tables(flat)
-            self.handle = _cabi.Plan(kind, src_hw, fwd, origin, rect, flat.out_w, flat.out_h, flat.channels)
+            self.handle = _cabi.Plan(kind, src_hw, fwd, origin, rect, flat.out_w, flat.out_h, flat.channels,
+                                     maps=plan_maps(flat))
             if self.feather_log2:
                 self.handle.set_feather(self.feather_log2)
         self.cams = [l.cam for l in flat.layers]

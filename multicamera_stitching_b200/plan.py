@@ -16,8 +16,10 @@ import numpy as np
 
 LAYER_COPY = 0
 LAYER_WARP = 1
+LAYER_REMAP = 2   # coordinates from a fixed-point map pair (prewarp.py), not from a homography
 
-Layer = namedtuple("Layer", "cam kind H ox oy rect src_hw")
+# ``map``: for LAYER_REMAP the (int16 H x W x 2, uint16 H x W) pair cv2.convertMaps produces
+Layer = namedtuple("Layer", "cam kind H ox oy rect src_hw map", defaults=(None,))
 FlatPlan = namedtuple("FlatPlan", "layers out_w out_h channels ndim")
 
 
@@ -135,3 +137,9 @@ def plan_tables(flat):
     for i, l in enumerate(flat.layers):
         fwd[i] = np.eye(3).ravel() if l.H is None else np.asarray(l.H, dtype=np.float64).ravel()
     return kind, src_hw, fwd, origin, rect
+
+
+def plan_maps(flat):
+    """Per-layer map pairs for ``mcs_plan_create_maps`` (None when no layer has one)."""
+    maps = [l.map for l in flat.layers]
+    return maps if any(m is not None for m in maps) else None
