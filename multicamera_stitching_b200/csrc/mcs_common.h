@@ -98,6 +98,10 @@ struct mcs_plan {
     long long* d_strip_prefix;   // n_strips + 1 running pixel counts
     int n_strips;
     long long strip_pixels;
+    // feather: plan-time sample table of the band pixels (mcs_stitch.cu), nullptr = evaluate on the fly
+    int2* d_band_xy;         // strip_pixels output coordinates
+    unsigned char* d_band_cnt;   // samples per band pixel (<= n_layers)
+    int4* d_band_ent;        // [n_layers][strip_pixels] {X, Y, layer, weight of the value so far}
     int force_variant;       // 0 = automatic, 1 = gather, 2 = tiled (diagnostics)
     // tiled variant
     int tiled_ok;            // tile table built and every box within limits
@@ -137,6 +141,11 @@ bool mcs_invert3x3(const double* m, double* out);
 // problem it leaves tiled_ok = 0 with the reason in tiled_why and the gather variant is used.
 void mcs_plan_build_tiles(mcs_plan* plan);
 void mcs_plan_free_tiles(mcs_plan* plan);
+
+// Feather mode: builds / frees the plan-time sample table of the band pixels (mcs_stitch.cu).  A
+// failure to build leaves the table empty; the on-the-fly band kernel then serves the mode.
+void mcs_feather_build_table(mcs_plan* plan);
+void mcs_feather_free_table(mcs_plan* plan);
 
 // Tiled variant (mcs_stitch_tiled.cu): why it cannot serve a call (nullptr = it can), and its launch.
 const char* mcs_tiled_blocker(const mcs_plan* plan, const uint8_t* const* src, const int64_t* pitch,

@@ -207,6 +207,7 @@ extern "C" int mcs_plan_create_maps(mcs_plan** out, int n_layers, int channels,
 
 extern "C" int mcs_plan_destroy(mcs_plan* plan) {
     if (!plan) return MCS_OK;
+    mcs_feather_free_table(plan);
     if (plan->d_strips) cudaFree(plan->d_strips);
     if (plan->d_strip_prefix) cudaFree(plan->d_strip_prefix);
     mcs_plan_free_tiles(plan);
@@ -231,6 +232,7 @@ extern "C" const char* mcs_plan_tiled_status(const mcs_plan* plan) {
 extern "C" int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan) { return plan ? plan->grid_ctas_per_sm : 0; }
 
 static void free_strips(mcs_plan* plan) {
+    mcs_feather_free_table(plan);
     if (plan->d_strips) cudaFree(plan->d_strips);
     if (plan->d_strip_prefix) cudaFree(plan->d_strip_prefix);
     plan->d_strips = nullptr;
@@ -298,5 +300,6 @@ extern "C" int mcs_plan_set_feather(mcs_plan* plan, int feather_log2) {
         plan->strip_pixels = prefix[n];
     }
     plan->feather_log2 = feather_log2;
+    mcs_feather_build_table(plan);
     return MCS_OK;
 }

@@ -14,6 +14,7 @@
 // The float64 operations use the __d*_rn intrinsics, which the compiler never contracts.
 #include "mcs_device.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 struct LayerArgs {
@@ -233,6 +234,111 @@ mcs_feather_band_kernel(const __grid_constant__ StitchArgs a, const int4* __rest
     for (int c = 0; c < C; ++c) out[c] = (uint8_t)v[c];
 }
 
+// Plan-time form of the same evaluation.  The chain a band pixel walks (owner layer, then every
+// outer layer whose pasted rectangle border is closer than F and whose warp touches its source
+// here) does not depend on the frame, and neither do the float64 source coordinates: one thread
+// per band pixel records them once (mcs_feather_table_kernel), entry e of pixel i at
+// ent[e * total + i] = {X, Y, layer, a} with a = weight of the value blended so far (F for the
+// first entry).  Per launch, mcs_feather_apply_kernel gives each thread one band pixel and
+// FEATHER_FPT consecutive frames: every entry is read once for those frames and its gathers are
+// independent across them.
+#define FEATHER_FPT 8
+
+__device__ __forceinline__ void band_pixel(const int4* __restrict__ strips, const long long* __restrict__ prefix,
+                                           int n_strips, long long i, int& x, int& y) {
+    int s = 0;
+    while (s + 1 < n_strips && prefix[s + 1] <= i) ++s;
+    const int4 r = strips[s];
+    const int w = r.z - r.x;
+    const int j = (int)(i - prefix[s]);
+    y = r.y + j / w;
+    x = r.x + j % w;
+}
+
+__global__ void __launch_bounds__(256)
+mcs_feather_table_kernel(const __grid_constant__ StitchArgs a, const int4* __restrict__ strips,
+                         const long long* __restrict__ prefix, int n_strips, int feather_log2,
+                         int2* __restrict__ band_xy, unsigned char* __restrict__ band_cnt,
+                         int4* __restrict__ band_ent) {
+    const long long total = prefix[n_strips];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int x, y;
+    band_pixel(strips, prefix, n_strips, i, x, y);
+    const int F = 1 << feather_log2;
+    band_xy[i] = make_int2(x, y);
+    int n = 0;
+    const int m = find_owner(a, x, y);
+    if (m >= 0) {
+        for (int k = m; k < a.n_layers; ++k) {
+            const McsLayer& g = a.L[k].g;
+            int d = F;
+            if (k > m) {
+                const McsLayer& in = a.L[k - 1].g;   // the rectangle pasted at stage k
+                d = min(min(x - in.rx0, in.rx1 - 1 - x), min(y - in.ry0, in.ry1 - 1 - y)) + 1;
+                if (d >= F) break;
+            }
+            const int xl = x - g.ox, yl = y - g.oy;
+            int X, Y;
+            bool touched = true;
+            if (g.kind == MCS_LAYER_COPY) {
+                X = xl * 32;
+                Y = yl * 32;
+            } else {
+                layer_coords(g, xl, yl, X, Y);
+                const int sx = sat16(X >> 5), sy = sat16(Y >> 5);
+                touched = ((unsigned)sx < (unsigned)g.src_w || (unsigned)(sx + 1) < (unsigned)g.src_w) &&
+                          ((unsigned)sy < (unsigned)g.src_h || (unsigned)(sy + 1) < (unsigned)g.src_h);
+            }
+            if (k == m || touched) band_ent[(size_t)n++ * total + i] = make_int4(X, Y, k, d);
+        }
+    }
+    band_cnt[i] = (unsigned char)n;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+mcs_feather_apply_kernel(const __grid_constant__ StitchArgs a, const int2* __restrict__ band_xy,
+                         const unsigned char* __restrict__ band_cnt, const int4* __restrict__ band_ent,
+                         long long total, int feather_log2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int f0 = blockIdx.y * FEATHER_FPT;
+    const int nf = min(FEATHER_FPT, a.n_frames - f0);
+    const int n = band_cnt[i];
+    const int2 xy = band_xy[i];
+    const int F = 1 << feather_log2;
+    int v[FEATHER_FPT][C];
+#pragma unroll
+    for (int f = 0; f < FEATHER_FPT; ++f)
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[f][c] = 0;
+    for (int e = 0; e < n; ++e) {
+        const int4 ent = __ldg(band_ent + (size_t)e * total + i);
+        const LayerArgs& L = a.L[ent.z];
+        const uint8_t* src = L.src + (long long)f0 * L.frame_stride;
+        const int d = ent.w;
+#pragma unroll
+        for (int f = 0; f < FEATHER_FPT; ++f) {
+            if (f < nf) {
+                int w[C];
+                sample_u8<C>(src + (long long)f * L.frame_stride, L.pitch, L.g.src_w, L.g.src_h, ent.x, ent.y, w);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    v[f][c] = e == 0 ? w[c] : (d * v[f][c] + (F - d) * w[c] + (F >> 1)) >> feather_log2;
+            }
+        }
+    }
+    uint8_t* out = a.dst + (long long)f0 * a.dst_frame_stride + (long long)xy.y * a.dst_pitch + (long long)xy.x * C;
+#pragma unroll
+    for (int f = 0; f < FEATHER_FPT; ++f) {
+        if (f < nf) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[(long long)f * a.dst_frame_stride + c] = (uint8_t)v[f][c];
+        }
+    }
+}
+
 // --------------------------------------------------------------------------------------------
 static int fill_args(const mcs_plan* plan, StitchArgs& a, const uint8_t* const* src,
                      const int64_t* src_pitch, const int64_t* src_frame_stride, int n_frames,
@@ -311,6 +417,18 @@ extern "C" int mcs_stitch_u8(const mcs_plan* plan_c, const uint8_t* const* src,
         fill_args(plan, a, src, src_pitch_bytes, src_frame_stride, n_frames, dst, dst_pitch_bytes,
                   dst_frame_stride);
         const long long total = plan->strip_pixels;
+        if (plan->d_band_ent) {
+            dim3 tgrid((unsigned)((total + 255) / 256), (n_frames + FEATHER_FPT - 1) / FEATHER_FPT, 1);
+            switch (plan->channels) {
+                case 1: mcs_feather_apply_kernel<1><<<tgrid, 256, 0, stream>>>(a, plan->d_band_xy, plan->d_band_cnt, plan->d_band_ent, total, plan->feather_log2); break;
+                case 3: mcs_feather_apply_kernel<3><<<tgrid, 256, 0, stream>>>(a, plan->d_band_xy, plan->d_band_cnt, plan->d_band_ent, total, plan->feather_log2); break;
+                default: mcs_feather_apply_kernel<4><<<tgrid, 256, 0, stream>>>(a, plan->d_band_xy, plan->d_band_cnt, plan->d_band_ent, total, plan->feather_log2); break;
+            }
+            mcs_count_launch(1);
+            MCS_CHECK_CUDA(cudaGetLastError());
+            plan->last_variant = 3;
+            return MCS_OK;
+        }
         dim3 grid((unsigned)((total + 255) / 256), 1, n_frames);
         switch (plan->channels) {
             case 1: mcs_feather_band_kernel<1><<<grid, 256, 0, stream>>>(a, plan->d_strips, plan->d_strip_prefix, plan->n_strips, plan->feather_log2); break;
@@ -347,4 +465,42 @@ extern "C" int mcs_plan_owned_pixels(const mcs_plan* plan, int64_t* owned_host, 
     }
     cudaFree(d);
     return rc;
+}
+
+void mcs_feather_free_table(mcs_plan* plan) {
+    if (plan->d_band_xy) cudaFree(plan->d_band_xy);
+    if (plan->d_band_cnt) cudaFree(plan->d_band_cnt);
+    if (plan->d_band_ent) cudaFree(plan->d_band_ent);
+    plan->d_band_xy = nullptr;
+    plan->d_band_cnt = nullptr;
+    plan->d_band_ent = nullptr;
+}
+
+void mcs_feather_build_table(mcs_plan* plan) {
+    mcs_feather_free_table(plan);
+    const long long total = plan->strip_pixels;
+    if (plan->feather_log2 <= 0 || plan->n_strips <= 0 || total <= 0) return;
+    const size_t ent_bytes = sizeof(int4) * (size_t)plan->n_layers * (size_t)total;
+    if (ent_bytes > ((size_t)2 << 30)) return;   // very wide bands: evaluate on the fly instead
+    {
+        const char* env = getenv("MCS_FEATHER_TABLE");   // "0": keep the on-the-fly band kernel (tests)
+        if (env && env[0] == '0') return;
+    }
+    cudaError_t e = cudaMalloc(&plan->d_band_xy, sizeof(int2) * (size_t)total);
+    if (e == cudaSuccess) e = cudaMalloc(&plan->d_band_cnt, (size_t)total);
+    if (e == cudaSuccess) e = cudaMalloc(&plan->d_band_ent, ent_bytes);
+    if (e == cudaSuccess) {
+        StitchArgs a;
+        fill_args(plan, a, nullptr, nullptr, nullptr, 1, nullptr, 0, 0);
+        mcs_feather_table_kernel<<<(unsigned)((total + 255) / 256), 256>>>(
+            a, plan->d_strips, plan->d_strip_prefix, plan->n_strips, plan->feather_log2, plan->d_band_xy,
+            plan->d_band_cnt, plan->d_band_ent);
+        mcs_count_launch(1);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        mcs_feather_free_table(plan);
+    }
 }

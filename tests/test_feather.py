@@ -61,6 +61,26 @@ def test_feather_kernel_matches_specification(cuda_device, n, h, w, c, log2):
 
 
 @pytest.mark.gpu
+def test_feather_on_the_fly_band_kernel_and_many_frames(cuda_device, monkeypatch):
+    """The plan-time sample table (default) and the on-the-fly band kernel (tables over 2 GB,
+    or $MCS_FEATHER_TABLE=0) give the same panoramas; 11 frames = one full and one partial
+    group of the table kernel's 8 frames per thread."""
+    import torch
+    n, h, w, c, log2 = 4, 90, 160, 3, 3
+    st, states, labels, images = synthetic_chain(n, h, w, c, kind="noise", xoffset=2, yoffset=7)
+    sets = [synthetic_chain(n, h, w, c, kind="noise", frame_index=f)[3] for f in range(11)]
+    batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
+    refs = [feather_model.feather_chain(states, labels, s, log2) for s in sets]
+    for table in ("1", "0"):
+        monkeypatch.setenv("MCS_FEATHER_TABLE", table)
+        st.__dict__.pop("_engine", None)          # new plan: the switch is read when the plan is built
+        st.feather_log2 = log2
+        out = st.stitch_batch(batch).cpu().numpy()
+        for f in range(11):
+            assert np.array_equal(out[f], refs[f]), (table, f)
+
+
+@pytest.mark.gpu
 def test_feather_refuses_super_mode_plans(cuda_device):
     from multicamera_stitching_b200.plan import PlanUnsupported
     st, states, labels, images = synthetic_chain(3, 120, 200, 3, super_mode=True)
