@@ -30,6 +30,9 @@ pytestmark = pytest.mark.gpu
     ((1, 1, 3), (9, 5)),
     ((2160, 3840, 3), (1920, 1080)),  # 4K -> 1080p (area kernel)
     ((1080, 1920, 3), (3840, 2160)),
+    ((600, 1000, 3), (100, 60)),      # 10 x decimation
+    ((300, 403), (200, 100)),         # one-channel rows that are not a multiple of 4 bytes
+    ((64, 50, 3), (300, 300)),        # upscale across several tiles from a narrow source
 ])
 def test_resize_kernel_equals_cv2(cuda_device, shape, dsize):
     rng = np.random.default_rng(hash((shape, dsize)) % (2 ** 32))
