@@ -94,6 +94,90 @@ mcs_resize_linear_kernel(const __grid_constant__ ResizeArgs a) {
     }
 }
 
+// Separable form for the general (non-area) case.  A CTA of 256 threads produces a 128 x 16 output
+// tile in two phases through shared memory:
+//   1. horizontal pass: for every source row the tile needs and every output column, h >> 4 (at
+//      most 255 * 2048 >> 4 = 32640, a uint16) - thread t owns column t & 127, so its column
+//      coefficients are computed once and the byte taps of a warp fall into one or two cache lines;
+//   2. vertical pass: a thread takes 4 adjacent pixels of two tile rows, 8-byte reads of the two
+//      source rows' h values, OpenCV's (((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2.
+// Every source byte is fetched once per tile row it serves instead of once per output pixel.
+#define RSEP_TW 128
+#define RSEP_TH 16
+#define RSEP_SMEM_MAX (40 * 1024)
+
+template <int C>
+__global__ void __launch_bounds__(256)
+mcs_resize_sep_kernel(const __grid_constant__ ResizeArgs a) {
+    extern __shared__ __align__(16) uint16_t hbuf[];   // [rows][RSEP_TW * C]
+    const int x0 = blockIdx.x * RSEP_TW, y0 = blockIdx.y * RSEP_TH;
+    const int tid = threadIdx.x;
+    const uint8_t* src = a.src + (long long)blockIdx.z * a.src_frame_stride;
+    const int y_last = min(y0 + RSEP_TH, a.dst_h) - 1;
+    int ry0, ry1;
+    {
+        int s0, s1, w0, w1;
+        linear_coef(y0, a.scale_y, a.src_h, false, s0, w0, w1);
+        linear_coef(y_last, a.scale_y, a.src_h, false, s1, w0, w1);
+        ry0 = max(0, min(a.src_h - 1, s0));
+        ry1 = max(0, min(a.src_h - 1, s1 + 1));
+    }
+    constexpr int ROW = RSEP_TW * C;   // uint16 per staged row
+    {   // phase 1
+        const int col = tid & (RSEP_TW - 1);
+        const int x = min(x0 + col, a.dst_w - 1);
+        int sx, a0, a1;
+        linear_coef(x, a.scale_x, a.src_w, true, sx, a0, a1);
+        const int o0 = sx * C, o1 = min(sx + 1, a.src_w - 1) * C;
+        for (int r = ry0 + (tid >> 7); r <= ry1; r += 2) {
+            const uint8_t* row = src + (long long)r * a.src_pitch;
+            uint16_t* h = hbuf + (r - ry0) * ROW + col * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                h[c] = (uint16_t)((__ldg(row + o0 + c) * a0 + __ldg(row + o1 + c) * a1) >> 4);
+        }
+    }
+    __syncthreads();
+    // phase 2
+    const int lane = tid & 31, warp = tid >> 5;
+    const int x_first = x0 + 4 * lane;
+    if (x_first >= a.dst_w) return;
+    const int n_px = min(4, a.dst_w - x_first);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int y = y0 + warp + 8 * half;
+        if (y >= a.dst_h) break;
+        int sy, b0, b1;
+        linear_coef(y, a.scale_y, a.src_h, false, sy, b0, b1);
+        const int r0 = max(0, min(a.src_h - 1, sy)) - ry0, r1 = max(0, min(a.src_h - 1, sy + 1)) - ry0;
+        // 4 pixels x C values = 4 * C uint16 = C 8-byte words per source row
+        const uint2* h0 = reinterpret_cast<const uint2*>(hbuf + r0 * ROW + 4 * lane * C);
+        const uint2* h1 = reinterpret_cast<const uint2*>(hbuf + r1 * ROW + 4 * lane * C);
+        uint8_t px[4 * C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const uint2 u = h0[k], v = h1[k];
+            const uint32_t uu[2] = {u.x, u.y}, vv[2] = {v.x, v.y};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int p0 = (uu[j >> 1] >> (16 * (j & 1))) & 0xffff, p1 = (vv[j >> 1] >> (16 * (j & 1))) & 0xffff;
+                px[4 * k + j] = (uint8_t)((((b0 * p0) >> 16) + ((b1 * p1) >> 16) + 2) >> 2);
+            }
+        }
+        uint8_t* out = a.dst + (long long)blockIdx.z * a.dst_frame_stride + (long long)y * a.dst_pitch +
+                       (long long)x_first * C;
+        if (n_px == 4 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+            for (int wd = 0; wd < C; ++wd)
+                o32[wd] = (uint32_t)px[4 * wd] | ((uint32_t)px[4 * wd + 1] << 8) | ((uint32_t)px[4 * wd + 2] << 16) |
+                          ((uint32_t)px[4 * wd + 3] << 24);
+        } else {
+            for (int b = 0; b < n_px * C; ++b) out[b] = px[b];
+        }
+    }
+}
+
 extern "C" int mcs_resize_linear_u8(const uint8_t* src, int src_w, int src_h, int64_t src_pitch_bytes,
                                     int64_t src_frame_stride, uint8_t* dst, int dst_w, int dst_h,
                                     int64_t dst_pitch_bytes, int64_t dst_frame_stride, int channels,
@@ -122,9 +206,24 @@ extern "C" int mcs_resize_linear_u8(const uint8_t* src, int src_w, int src_h, in
     a.scale_y = 1.0 / inv_y;
     a.src_w = src_w; a.src_h = src_h; a.dst_w = dst_w; a.dst_h = dst_h;
     a.area2 = (a.scale_x == 2.0 && a.scale_y == 2.0) ? 1 : 0;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    // separable two-phase kernel unless the tile's source rows exceed the shared-memory budget
+    // (decimation beyond ~3 x) or the area kernel applies
+    const long long sep_rows = (long long)(RSEP_TH * a.scale_y) + 4;
+    const long long sep_smem = sep_rows * RSEP_TW * channels * 2;
+    if (!a.area2 && sep_smem <= RSEP_SMEM_MAX) {
+        const dim3 sgrid((dst_w + RSEP_TW - 1) / RSEP_TW, (dst_h + RSEP_TH - 1) / RSEP_TH, n_frames);
+        switch (channels) {
+            case 1: mcs_resize_sep_kernel<1><<<sgrid, 256, (size_t)sep_smem, stream>>>(a); break;
+            case 3: mcs_resize_sep_kernel<3><<<sgrid, 256, (size_t)sep_smem, stream>>>(a); break;
+            default: mcs_resize_sep_kernel<4><<<sgrid, 256, (size_t)sep_smem, stream>>>(a); break;
+        }
+        mcs_count_launch(1);
+        MCS_CHECK_CUDA(cudaGetLastError());
+        return MCS_OK;
+    }
     const dim3 block(32, 8, 1);
     const dim3 grid((dst_w + 127) / 128, (dst_h + 7) / 8, n_frames);
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
     switch (channels) {
         case 1: mcs_resize_linear_kernel<1><<<grid, block, 0, stream>>>(a); break;
         case 3: mcs_resize_linear_kernel<3><<<grid, block, 0, stream>>>(a); break;
