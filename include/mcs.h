@@ -123,6 +123,36 @@ int mcs_plan_destroy(mcs_plan* plan);
 int mcs_plan_owned_pixels(const mcs_plan* plan, int64_t* owned_host, void* cuda_stream);
 
 /*
+ * mcs_plan_source_windows - per layer, the half-open window {x0, y0, x1, y1} of SOURCE pixels
+ * that the layer's owned output pixels read (host int32 xyxy[n_layers*4]).  Source bytes outside
+ * the window cannot influence the panorama - they belong to the part of the camera that the
+ * reference's paste (StitcherClass.py:240-241) overwrites - so a host-facing caller needs to
+ * bring only the window onto the device.  Whole frames when the windows are not known (no tile
+ * table, feather mode).
+ */
+int mcs_plan_source_windows(const mcs_plan* plan, int32_t* xyxy);
+
+/*
+ * mcs_plan_source_spans - the same information at finer grain: for every band of `band_rows`
+ * source rows of layer `layer`, the half-open column range {x0, x1} its owned output pixels read
+ * (host int32 x0x1[ceil(src_h / band_rows) * 2]; x0 == x1: nothing is read from the band).  A
+ * camera whose visible part is not a rectangle (a sheared seam) is covered far more tightly by a
+ * few row bands than by one window.
+ */
+int mcs_plan_source_spans(const mcs_plan* plan, int layer, int band_rows, int32_t* x0x1);
+
+/*
+ * mcs_copy_window_u8 - copy the byte window [x_byte0, x_byte0 + width_bytes) x [y0, y0 + rows)
+ * of n_frames frames between two buffers of the same frame geometry (host or device, either
+ * direction; pinned host memory for an asynchronous copy), leaving everything outside the window
+ * untouched.  Plumbing for the host-facing sequence path: together with
+ * mcs_plan_source_windows it replaces the whole-frame upload in front of mcs_stitch_u8.
+ */
+int mcs_copy_window_u8(void* dst, int64_t dst_pitch_bytes, int64_t dst_frame_stride, const void* src,
+                       int64_t src_pitch_bytes, int64_t src_frame_stride, int64_t x_byte0,
+                       int64_t width_bytes, int y0, int rows, int n_frames, void* cuda_stream);
+
+/*
  * mcs_stitch_u8 - composite n_frames panoramas.
  *
  * Replaces, per frame, the whole Stitcher.stitch chain (StitcherClass.py:

@@ -22,7 +22,7 @@ ABI_VERSION = 1
 # every symbol include/mcs.h declares
 EXPORTS = (
     "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_create_maps", "mcs_plan_destroy",
-    "mcs_plan_owned_pixels", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_last_variant",
+    "mcs_plan_owned_pixels", "mcs_plan_source_windows", "mcs_plan_source_spans", "mcs_copy_window_u8", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_last_variant",
     "mcs_plan_force_variant",
     "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_launch_count",
     "mcs_match_hamming_top2", "mcs_ransac_homography", "mcs_resize_linear_u8",
@@ -73,6 +73,13 @@ def load(build_if_missing=False):
     lib.mcs_plan_destroy.argtypes = [_vp]
     lib.mcs_plan_owned_pixels.restype = ctypes.c_int
     lib.mcs_plan_owned_pixels.argtypes = [_vp, _c_i64p, _vp]
+    lib.mcs_plan_source_windows.restype = ctypes.c_int
+    lib.mcs_plan_source_windows.argtypes = [_vp, _c_i32p]
+    lib.mcs_plan_source_spans.restype = ctypes.c_int
+    lib.mcs_plan_source_spans.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _c_i32p]
+    lib.mcs_copy_window_u8.restype = ctypes.c_int
+    lib.mcs_copy_window_u8.argtypes = [_vp, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
     lib.mcs_stitch_u8.restype = ctypes.c_int
     lib.mcs_stitch_u8.argtypes = [_vp, ctypes.POINTER(_vp), _c_i64p, _c_i64p, ctypes.c_int, _vp,
                                   ctypes.c_int64, ctypes.c_int64, _vp]
@@ -119,6 +126,14 @@ def resize_linear_u8(src_ptr, src_w, src_h, src_pitch, src_frame_stride, dst_ptr
                                       int(src_frame_stride), _vp(int(dst_ptr)), int(dst_w), int(dst_h),
                                       int(dst_pitch), int(dst_frame_stride), int(channels), int(n_frames),
                                       _vp(int(stream))), "mcs_resize_linear_u8")
+
+
+def copy_window_u8(dst_ptr, dst_pitch, dst_frame_stride, src_ptr, src_pitch, src_frame_stride, x_byte0, width_bytes,
+                   y0, rows, n_frames, stream=0):
+    """Window copy between two frame buffers of the same geometry (include/mcs.h)."""
+    check(load().mcs_copy_window_u8(_vp(int(dst_ptr)), int(dst_pitch), int(dst_frame_stride), _vp(int(src_ptr)),
+                                    int(src_pitch), int(src_frame_stride), int(x_byte0), int(width_bytes), int(y0),
+                                    int(rows), int(n_frames), _vp(int(stream))), "mcs_copy_window_u8")
 
 
 def _i32(a):
@@ -200,6 +215,19 @@ class Plan(object):
             check(_lib.mcs_plan_owned_pixels(self._h, out, _vp(int(stream))), "mcs_plan_owned_pixels")
             self._owned = [int(out[k]) for k in range(self.n_layers)]
         return list(self._owned)
+
+    def source_windows(self):
+        """Per layer ``(x0, y0, x1, y1)``: the source pixels the layer's owned output pixels read."""
+        out = (ctypes.c_int32 * (4 * self.n_layers))()
+        check(_lib.mcs_plan_source_windows(self._h, out), "mcs_plan_source_windows")
+        return [tuple(int(out[4 * k + j]) for j in range(4)) for k in range(self.n_layers)]
+
+    def source_spans(self, layer, band_rows):
+        """``[(x0, x1), ...]`` per band of ``band_rows`` source rows of ``layer``."""
+        n = (int(self.src_hw[layer][0]) + band_rows - 1) // band_rows
+        out = (ctypes.c_int32 * (2 * n))()
+        check(_lib.mcs_plan_source_spans(self._h, int(layer), int(band_rows), out), "mcs_plan_source_spans")
+        return [(int(out[2 * b]), int(out[2 * b + 1])) for b in range(n)]
 
     def algorithmic_bytes(self, stream=0):
         """every output byte written once + one source

@@ -112,6 +112,9 @@ struct mcs_plan {
     McsLayer* d_layers;
     int2* d_maps[MCS_MAX_LAYERS];   // coordinate maps of the REMAP layers (owned by the plan)
     uint32_t* d_desc;        // per-pixel descriptors of the WARP tiles, 2048 words per tile (mcs_tiles.cu)
+    int src_win[MCS_MAX_LAYERS][4];   // per layer: source window {x0, y0, x1, y1} its owned pixels read
+    int src_win_valid;       // set with the tile table; otherwise the whole frame counts
+    int* h_row_span[MCS_MAX_LAYERS];   // host, per source row {x0, x1} of the pixels read (nullptr = unknown)
     int frame_block;         // frames per sweep of the tile table (mcs_launch_tiled)
     // cache of the TMA descriptors of the last call (keyed by the source table)
     unsigned char tmap_cache[MCS_MAX_LAYERS * 128 + 64];

@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <new>
+#include <limits.h>
 #include <string.h>
 #include <vector>
 
@@ -213,6 +214,76 @@ extern "C" int mcs_plan_destroy(mcs_plan* plan) {
     mcs_plan_free_tiles(plan);
     free_maps(plan);
     delete plan;
+    return MCS_OK;
+}
+
+extern "C" int mcs_plan_source_windows(const mcs_plan* plan, int32_t* xyxy) {
+    MCS_CHECK_ARG(plan != nullptr && xyxy != nullptr, "mcs_plan_source_windows: NULL argument");
+    // The feather band samples outer cameras inside the pasted rectangles, i.e. outside the
+    // pixels they own: there every frame counts in full.
+    const bool known = plan->src_win_valid && plan->feather_log2 == 0;
+    for (int k = 0; k < plan->n_layers; ++k) {
+        xyxy[4 * k + 0] = known ? plan->src_win[k][0] : 0;
+        xyxy[4 * k + 1] = known ? plan->src_win[k][1] : 0;
+        xyxy[4 * k + 2] = known ? plan->src_win[k][2] : plan->layers[k].src_w;
+        xyxy[4 * k + 3] = known ? plan->src_win[k][3] : plan->layers[k].src_h;
+    }
+    return MCS_OK;
+}
+
+extern "C" int mcs_plan_source_spans(const mcs_plan* plan, int layer, int band_rows, int32_t* x0x1) {
+    MCS_CHECK_ARG(plan != nullptr && x0x1 != nullptr && band_rows > 0, "mcs_plan_source_spans: bad argument");
+    MCS_CHECK_ARG(layer >= 0 && layer < plan->n_layers, "mcs_plan_source_spans: layer %d outside 0..%d", layer,
+                  plan->n_layers - 1);
+    const McsLayer& L = plan->layers[layer];
+    const int n_bands = (L.src_h + band_rows - 1) / band_rows;
+    const int* span = plan->h_row_span[layer];
+    const bool known = plan->src_win_valid && plan->feather_log2 == 0 && span != nullptr;
+    for (int b = 0; b < n_bands; ++b) {
+        int x0 = known ? INT_MAX : 0, x1 = known ? INT_MIN : L.src_w;
+        for (int r = b * band_rows; known && r < (b + 1) * band_rows && r < L.src_h; ++r) {
+            x0 = span[2 * r] < x0 ? span[2 * r] : x0;
+            x1 = span[2 * r + 1] > x1 ? span[2 * r + 1] : x1;
+        }
+        if (x1 <= x0) x0 = x1 = 0;
+        x0x1[2 * b] = x0 < 0 ? 0 : x0;
+        x0x1[2 * b + 1] = x1 > L.src_w ? L.src_w : x1;
+    }
+    return MCS_OK;
+}
+
+// Strided frame-window copy in either direction (one cudaMemcpy3DAsync: width x rows x frames).
+extern "C" int mcs_copy_window_u8(void* dst, int64_t dst_pitch_bytes, int64_t dst_frame_stride, const void* src,
+                                  int64_t src_pitch_bytes, int64_t src_frame_stride, int64_t x_byte0,
+                                  int64_t width_bytes, int y0, int rows, int n_frames, void* cuda_stream) {
+    MCS_CHECK_ARG(dst != nullptr && src != nullptr, "mcs_copy_window_u8: NULL buffer");
+    MCS_CHECK_ARG(x_byte0 >= 0 && width_bytes >= 0 && y0 >= 0 && rows >= 0 && n_frames >= 0,
+                  "mcs_copy_window_u8: negative extent");
+    if (width_bytes == 0 || rows == 0 || n_frames == 0) return MCS_OK;
+    MCS_CHECK_ARG(x_byte0 + width_bytes <= dst_pitch_bytes && x_byte0 + width_bytes <= src_pitch_bytes,
+                  "mcs_copy_window_u8: window wider than a row");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const bool as3d = n_frames == 1 || (dst_frame_stride % dst_pitch_bytes == 0 && src_frame_stride % src_pitch_bytes == 0);
+    if (as3d) {
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        const size_t dst_rows = n_frames == 1 ? (size_t)(y0 + rows) : (size_t)(dst_frame_stride / dst_pitch_bytes);
+        const size_t src_rows = n_frames == 1 ? (size_t)(y0 + rows) : (size_t)(src_frame_stride / src_pitch_bytes);
+        p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), (size_t)src_pitch_bytes, (size_t)src_pitch_bytes, src_rows);
+        p.dstPtr = make_cudaPitchedPtr(dst, (size_t)dst_pitch_bytes, (size_t)dst_pitch_bytes, dst_rows);
+        p.srcPos = make_cudaPos((size_t)x_byte0, (size_t)y0, 0);
+        p.dstPos = make_cudaPos((size_t)x_byte0, (size_t)y0, 0);
+        p.extent = make_cudaExtent((size_t)width_bytes, (size_t)rows, (size_t)n_frames);
+        p.kind = cudaMemcpyDefault;
+        MCS_CHECK_CUDA(cudaMemcpy3DAsync(&p, stream));
+        return MCS_OK;
+    }
+    for (int f = 0; f < n_frames; ++f) {
+        const char* s = static_cast<const char*>(src) + (size_t)f * src_frame_stride + (size_t)y0 * src_pitch_bytes + x_byte0;
+        char* d = static_cast<char*>(dst) + (size_t)f * dst_frame_stride + (size_t)y0 * dst_pitch_bytes + x_byte0;
+        MCS_CHECK_CUDA(cudaMemcpy2DAsync(d, (size_t)dst_pitch_bytes, s, (size_t)src_pitch_bytes, (size_t)width_bytes,
+                                         (size_t)rows, cudaMemcpyDefault, stream));
+    }
     return MCS_OK;
 }
 

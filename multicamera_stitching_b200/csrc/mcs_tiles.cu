@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <vector>
+#include <limits.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -157,6 +158,11 @@ void mcs_plan_free_tiles(mcs_plan* plan) {
     if (plan->d_desc) cudaFree(plan->d_desc);
     plan->d_desc = nullptr;
     free(plan->h_cum);
+    for (int k = 0; k < MCS_MAX_LAYERS; ++k) {
+        free(plan->h_row_span[k]);
+        plan->h_row_span[k] = nullptr;
+    }
+    plan->src_win_valid = 0;
     plan->d_tiles = nullptr;
     plan->d_layers = nullptr;
     plan->d_sched = nullptr;
@@ -178,6 +184,7 @@ static int tile_cost(const McsTile& t) {
 
 void mcs_plan_build_tiles(mcs_plan* plan) {
     plan->tiled_ok = 0;
+    plan->src_win_valid = 0;
     plan->tiled_why[0] = 0;
     const int C = plan->channels;
     if (plan->out_w == 0 || plan->out_h == 0) { why(plan, "empty panorama"); return; }
@@ -245,7 +252,25 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
 
     // classify, place the boxes, size them per layer
     int bw4[MCS_MAX_LAYERS], bh[MCS_MAX_LAYERS];
-    for (int k = 0; k < MCS_MAX_LAYERS; ++k) bw4[k] = bh[k] = 0;
+    int win[MCS_MAX_LAYERS][4];   // source pixels the owned tiles of a layer read: x0, y0, x1, y1
+    for (int k = 0; k < MCS_MAX_LAYERS; ++k) {
+        bw4[k] = bh[k] = 0;
+        win[k][0] = win[k][1] = INT_MAX;
+        win[k][2] = win[k][3] = INT_MIN;
+    }
+    std::vector<int> span[MCS_MAX_LAYERS];   // per source row {x0, x1}
+    for (int k = 0; k < plan->n_layers; ++k) {
+        span[k].resize(2 * (size_t)plan->layers[k].src_h);
+        for (int r = 0; r < plan->layers[k].src_h; ++r) { span[k][2 * r] = INT_MAX; span[k][2 * r + 1] = INT_MIN; }
+    }
+    auto grow = [&](int k, int x0, int y0, int x1, int y1) {
+        win[k][0] = std::min(win[k][0], x0); win[k][1] = std::min(win[k][1], y0);
+        win[k][2] = std::max(win[k][2], x1); win[k][3] = std::max(win[k][3], y1);
+        for (int r = std::max(0, y0); r < y1 && r < plan->layers[k].src_h; ++r) {
+            span[k][2 * r] = std::min(span[k][2 * r], x0);
+            span[k][2 * r + 1] = std::max(span[k][2 * r + 1], x1);
+        }
+    };
     for (int i = 0; i < n_tiles; ++i) {
         McsTile& t = tiles[i];
         if (t.layer < 0) continue;
@@ -257,6 +282,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             t.by = t.y0 - L.oy;
             need_w = (end_byte + 3) / 4 - t.bx + 1;   // +1: the realigning write-out reads one word ahead
             need_h = t.h;
+            grow(t.layer, t.cx0 + t.c0 - L.ox, t.y0 - L.oy, t.cx0 + t.c1 - L.ox, t.y0 - L.oy + t.h);
         } else if (!bounds[i].touched) {
             t.cls = MCS_TILE_ZERO;
             continue;
@@ -266,6 +292,8 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             t.by = b.min_sy;
             need_w = ((b.max_sx + 2) * C + 3) / 4 - t.bx + 1;   // taps sx, sx+1 and one spare word
             need_h = b.max_sy + 2 - b.min_sy;
+            grow(t.layer, std::max(0, b.min_sx), std::max(0, b.min_sy), std::min(L.src_w, b.max_sx + 2),
+                 std::min(L.src_h, b.max_sy + 2));
         }
         bw4[t.layer] = std::max(bw4[t.layer], need_w);
         bh[t.layer] = std::max(bh[t.layer], need_h);
@@ -354,5 +382,14 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
     plan->d_layers = d_layers;
     plan->n_tiles = n_tiles;
     plan->box_bytes = (box_bytes + 127) & ~127;
+    for (int k = 0; k < plan->n_layers; ++k) {
+        const bool none = win[k][0] >= win[k][2] || win[k][1] >= win[k][3];
+        for (int j = 0; j < 4; ++j) plan->src_win[k][j] = none ? 0 : win[k][j];
+    }
+    for (int k = 0; k < plan->n_layers; ++k) {
+        plan->h_row_span[k] = static_cast<int*>(malloc(sizeof(int) * span[k].size() + 1));
+        if (plan->h_row_span[k]) memcpy(plan->h_row_span[k], span[k].data(), sizeof(int) * span[k].size());
+    }
+    plan->src_win_valid = 1;
     plan->tiled_ok = 1;
 }

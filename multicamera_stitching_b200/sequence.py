@@ -9,6 +9,8 @@ only its own output goes back to the host (SURVEY.md section 8 row e).
 """
 import torch
 
+from . import _cabi
+
 
 def shard_range(n_frames, world_size, rank):
     """Contiguous frame range ``[lo, hi)`` of ``rank``: sizes differ by at most
@@ -33,7 +35,7 @@ class SequencePipeline(object):
     tensor ``[F, H, W, C]``, ``host_out`` a pinned ``[F, H_out, W_out, C]``.
     """
 
-    def __init__(self, stitcher, img_shapes, device, chunk=4, depth=2):
+    def __init__(self, stitcher, img_shapes, device, chunk=4, depth=2, windows=True):
         self.stitcher = stitcher
         self.device = torch.device(device)
         self.labels = list(stitcher.img_labels)
@@ -54,8 +56,41 @@ class SequencePipeline(object):
                 self.slots.append(dict(src=src, dst=dst, ev_in=torch.cuda.Event(), ev_k=torch.cuda.Event(),
                                        ev_out=torch.cuda.Event(), used=False))
 
+        # Host -> device: only the part of every camera that can reach the panorama
+        # (mcs_plan_source_spans): per band of BAND source rows the column range the kernel reads,
+        # widened to 64-byte boundaries, neighbouring bands with the same range merged into one
+        # copy.  What is hidden under the pasted inner canvas is never read by the kernel and stays
+        # whatever the device buffer held.  ``windows=False`` uploads whole frames.
+        self.windows = []     # per camera: list of copies {b0, nbytes, y0, rows}
+        self.geometry = []    # per camera: (row bytes, rows)
+        layer_of = {l.cam: k for k, l in enumerate(self.plan.flat.layers)}
+        for c, shape in enumerate(img_shapes):
+            h, w = int(shape[0]), int(shape[1])
+            px = int(shape[2]) if len(shape) == 3 else 1
+            row = w * px
+            self.geometry.append((row, h))
+            if not windows:
+                self.windows.append([dict(b0=0, nbytes=row, y0=0, rows=h)])
+                continue
+            copies = []
+            if c in layer_of:
+                for b, (x0, x1) in enumerate(self.plan.handle.source_spans(layer_of[c], self.BAND)):
+                    if x1 <= x0:
+                        continue
+                    b0 = (x0 * px) // 64 * 64
+                    b1 = min(row, -(-(x1 * px) // 64) * 64)
+                    y0, rows = b * self.BAND, min(self.BAND, h - b * self.BAND)
+                    last = copies[-1] if copies else None
+                    if last and last["b0"] == b0 and last["nbytes"] == b1 - b0 and last["y0"] + last["rows"] == y0:
+                        last["rows"] += rows
+                    else:
+                        copies.append(dict(b0=b0, nbytes=b1 - b0, y0=y0, rows=rows))
+            self.windows.append(copies)
+
+    BAND = 64   # source rows per upload band
+
     def bytes_per_frame(self):
-        h2d = sum(int(s["src"][c][0].numel()) for s in self.slots[:1] for c in range(len(self.labels)))
+        h2d = sum(w["nbytes"] * w["rows"] for copies in self.windows for w in copies)
         d2h = int(self.slots[0]["dst"][0].numel())
         return h2d, d2h
 
@@ -78,7 +113,18 @@ class SequencePipeline(object):
                     if slot["used"]:
                         self.s_in.wait_event(slot["ev_k"])      # previous kernel done reading the slot
                     for c, label in enumerate(self.labels):
-                        slot["src"][c][:n].copy_(host_frames[label][f0:f0 + n], non_blocking=True)
+                        host = host_frames[label]
+                        row, h = self.geometry[c]
+                        copies = self.windows[c]
+                        if len(copies) == 1 and copies[0]["nbytes"] == row and copies[0]["rows"] == h:
+                            slot["src"][c][:n].copy_(host[f0:f0 + n], non_blocking=True)
+                            continue
+                        if copies and not host.is_contiguous():
+                            raise ValueError("host frames of %r must be contiguous" % (label,))
+                        fs = row * h
+                        for w in copies:
+                            _cabi.copy_window_u8(slot["src"][c].data_ptr(), row, fs, host.data_ptr() + f0 * fs, row, fs,
+                                                 w["b0"], w["nbytes"], w["y0"], w["rows"], n, self.s_in.cuda_stream)
                     slot["ev_in"].record(self.s_in)
                 with torch.cuda.stream(self.s_k):
                     self.s_k.wait_event(slot["ev_in"])

@@ -1,0 +1,55 @@
+"""GPU: the host-facing sequence path (``sequence.SequencePipeline``, what ``bench.py`` times as
+``e2e``) with window uploads: only the part of every camera that can reach the panorama is
+copied to the device (``mcs_plan_source_windows`` + ``mcs_copy_window_u8``).  The device slots are
+poisoned first, so a byte the kernel reads but the window does not cover would show up."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import compare_u8, synthetic_chain
+from multicamera_stitching_b200.sequence import SequencePipeline, pinned_like
+from oracle import stitcher_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,h,w,c", [(6, 270, 480, 3), (3, 180, 320, 1), (4, 120, 200, 4)])
+def test_pipeline_with_window_uploads_equals_the_cv2_chain(cuda_device, n, h, w, c):
+    st, states, labels, images = synthetic_chain(n, h, w, c, kind="noise")
+    shapes = [images[l].shape for l in labels]
+    F = 7
+    sets = [synthetic_chain(n, h, w, c, kind="noise", frame_index=f)[3] for f in range(F)]
+    host = {l: pinned_like((F,) + tuple(images[l].shape)) for l in labels}
+    for l in labels:
+        for f in range(F):
+            host[l][f].copy_(torch.from_numpy(sets[f][l]))
+    pipe = SequencePipeline(st, shapes, cuda_device, chunk=3, depth=2)
+    h2d, d2h = pipe.bytes_per_frame()
+    full = sum(int(np.prod(s)) for s in shapes)
+    assert 0 < h2d < full                       # overlapping cameras: some part is always hidden
+    wins = pipe.plan.handle.source_windows()
+    assert len(wins) == n and wins[0] == (0, 0, w, h)   # camera 0 is pasted whole
+    for k in range(n):                                   # the row-band spans refine the window
+        spans = [s for s in pipe.plan.handle.source_spans(k, 16) if s[1] > s[0]]
+        assert min(s[0] for s in spans) == wins[k][0] and max(s[1] for s in spans) == wins[k][2]
+    for slot in pipe.slots:                     # poison what the windows do not cover
+        for t in slot["src"]:
+            t.fill_(0xAB)
+    out = pinned_like((F,) + pipe.plan.out_shape())
+    assert pipe.run(host, out) == F
+    for f in range(F):
+        assert compare_u8(out[f].numpy(), stitcher_ref.stitch_chain(states, labels, sets[f])) == (0, 1.0)
+    # whole-frame uploads give the same panoramas
+    whole = SequencePipeline(st, shapes, cuda_device, chunk=3, depth=2, windows=False)
+    assert whole.bytes_per_frame()[0] == full
+    out2 = pinned_like((F,) + pipe.plan.out_shape())
+    whole.run(host, out2)
+    assert torch.equal(out, out2)
+
+
+def test_feather_mode_uploads_whole_frames(cuda_device):
+    st, states, labels, images = synthetic_chain(3, 120, 200, 3, kind="noise")
+    st.feather_log2 = 2
+    shapes = [images[l].shape for l in labels]
+    pipe = SequencePipeline(st, shapes, cuda_device, chunk=2, depth=2)
+    assert pipe.bytes_per_frame()[0] == sum(int(np.prod(s)) for s in shapes)
