@@ -49,6 +49,42 @@ class CompiledPlan(object):
         with torch.cuda.device(self.device):
             return self.handle.owned_pixels(torch.cuda.current_stream().cuda_stream)
 
+    # ---- what the host has to send ------------------------------------------
+    BAND = 64   # source rows per upload band
+
+    def upload_bands(self, whole=False):
+        """Per camera, the byte windows of a frame that can reach the panorama: a list of copies
+        ``{b0, nbytes, y0, rows}`` (bytes ``[b0, b0 + nbytes)`` of rows ``[y0, y0 + rows)``), from
+        ``mcs_plan_source_spans`` per band of ``BAND`` source rows, columns widened to 64-byte
+        boundaries, neighbouring bands with the same range merged.  What lies under the pasted
+        inner canvas (StitcherClass.py:240-241) is never read by the kernels, so a host-facing
+        caller need not upload it.  Returns ``{cam: (row_bytes, rows, copies)}``; ``whole=True``
+        (and feather mode) lists whole frames."""
+        key = bool(whole)
+        cache = self.__dict__.setdefault("_bands", {})
+        if key not in cache:
+            out = {}
+            for k, l in enumerate(self.flat.layers):
+                h, w = int(l.src_hw[0]), int(l.src_hw[1])
+                px = self.channels
+                row = w * px
+                copies = []
+                spans = [(0, w)] * (-(-h // self.BAND)) if whole else self.handle.source_spans(k, self.BAND)
+                for b, (x0, x1) in enumerate(spans):
+                    if x1 <= x0:
+                        continue
+                    b0 = (x0 * px) // 64 * 64
+                    b1 = min(row, -(-(x1 * px) // 64) * 64)
+                    y0, rows = b * self.BAND, min(self.BAND, h - b * self.BAND)
+                    last = copies[-1] if copies else None
+                    if last and last["b0"] == b0 and last["nbytes"] == b1 - b0 and last["y0"] + last["rows"] == y0:
+                        last["rows"] += rows
+                    else:
+                        copies.append(dict(b0=b0, nbytes=b1 - b0, y0=y0, rows=rows))
+                out[l.cam] = (row, h, copies)
+            cache[key] = out
+        return cache[key]
+
     # ---- launch -----------------------------------------------------------
     def _describe(self, t, batched):
         """(data_ptr, pitch_bytes, frame_stride_bytes) of a uint8 CUDA tensor
@@ -146,14 +182,27 @@ class CompositeEngine(object):
             self._plans[key] = CompiledPlan(flat, device, feather_log2) if flat is not None else None
         return self._plans[key]
 
-    def upload(self, cam, arr, device):
-        """Host frame -> (reused) device tensor on the current stream."""
+    def upload(self, cam, arr, device, bands=None):
+        """Host frame -> (reused) device tensor on the current stream.  ``bands`` =
+        ``CompiledPlan.upload_bands()[cam]``: only those byte windows of the frame are sent, the
+        rest of the device tensor keeps whatever it held (the kernels never read it)."""
         t = torch.from_numpy(np.ascontiguousarray(arr)) if isinstance(arr, np.ndarray) else arr.contiguous()
+        if t.dtype != torch.uint8:
+            raise TypeError("frames must be uint8, got %s" % (t.dtype,))
         key = (cam, tuple(t.shape), str(device))
         buf = self._staging.get(key)
         if buf is None:
             buf = torch.empty(t.shape, dtype=torch.uint8, device=device)
             self._staging[key] = buf
+        if bands is not None:
+            row, h, copies = bands
+            whole = len(copies) == 1 and copies[0]["nbytes"] == row and copies[0]["rows"] == h
+            if not whole and t.dim() in (2, 3) and int(t.shape[0]) == h and t.numel() == row * h:
+                stream = torch.cuda.current_stream().cuda_stream
+                for w in copies:
+                    _cabi.copy_window_u8(buf.data_ptr(), row, row * h, t.data_ptr(), row, row * h, w["b0"], w["nbytes"],
+                                         w["y0"], w["rows"], 1, stream)
+                return buf
         buf.copy_(t, non_blocking=True)
         return buf
 

@@ -57,37 +57,17 @@ class SequencePipeline(object):
                                        ev_out=torch.cuda.Event(), used=False))
 
         # Host -> device: only the part of every camera that can reach the panorama
-        # (mcs_plan_source_spans): per band of BAND source rows the column range the kernel reads,
-        # widened to 64-byte boundaries, neighbouring bands with the same range merged into one
-        # copy.  What is hidden under the pasted inner canvas is never read by the kernel and stays
-        # whatever the device buffer held.  ``windows=False`` uploads whole frames.
+        # (CompiledPlan.upload_bands: per band of source rows the column range the kernel reads).
+        # What is hidden under the pasted inner canvas is never read and stays whatever the device
+        # buffer held.  ``windows=False`` uploads whole frames.
+        bands = self.plan.upload_bands(whole=not windows)
         self.windows = []     # per camera: list of copies {b0, nbytes, y0, rows}
         self.geometry = []    # per camera: (row bytes, rows)
-        layer_of = {l.cam: k for k, l in enumerate(self.plan.flat.layers)}
         for c, shape in enumerate(img_shapes):
             h, w = int(shape[0]), int(shape[1])
-            px = int(shape[2]) if len(shape) == 3 else 1
-            row = w * px
+            row = w * (int(shape[2]) if len(shape) == 3 else 1)
             self.geometry.append((row, h))
-            if not windows:
-                self.windows.append([dict(b0=0, nbytes=row, y0=0, rows=h)])
-                continue
-            copies = []
-            if c in layer_of:
-                for b, (x0, x1) in enumerate(self.plan.handle.source_spans(layer_of[c], self.BAND)):
-                    if x1 <= x0:
-                        continue
-                    b0 = (x0 * px) // 64 * 64
-                    b1 = min(row, -(-(x1 * px) // 64) * 64)
-                    y0, rows = b * self.BAND, min(self.BAND, h - b * self.BAND)
-                    last = copies[-1] if copies else None
-                    if last and last["b0"] == b0 and last["nbytes"] == b1 - b0 and last["y0"] + last["rows"] == y0:
-                        last["rows"] += rows
-                    else:
-                        copies.append(dict(b0=b0, nbytes=b1 - b0, y0=y0, rows=rows))
-            self.windows.append(copies)
-
-    BAND = 64   # source rows per upload band
+            self.windows.append(bands[c][2] if c in bands else [])
 
     def bytes_per_frame(self):
         h2d = sum(w["nbytes"] * w["rows"] for copies in self.windows for w in copies)

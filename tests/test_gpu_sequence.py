@@ -53,3 +53,20 @@ def test_feather_mode_uploads_whole_frames(cuda_device):
     shapes = [images[l].shape for l in labels]
     pipe = SequencePipeline(st, shapes, cuda_device, chunk=2, depth=2)
     assert pipe.bytes_per_frame()[0] == sum(int(np.prod(s)) for s in shapes)
+
+
+def test_single_call_numpy_path_uploads_only_the_visible_windows(cuda_device):
+    """``Stitcher.stitch(images_dic)`` with numpy frames sends the same windows; the reused device
+    staging tensors keep stale bytes outside them, which must never reach a panorama."""
+    st, states, labels, images = synthetic_chain(5, 200, 360, 3, kind="noise")
+    assert compare_u8(st.stitch(images), stitcher_ref.stitch_chain(states, labels, images)) == (0, 1.0)
+    eng = st._engine_()
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    bands = plan.upload_bands()
+    sent = sum(w["nbytes"] * w["rows"] for _, _, copies in bands.values() for w in copies)
+    assert 0 < sent < sum(images[l].size for l in labels)
+    for t in eng._staging.values():
+        t.fill_(0x5A)
+    for f in (1, 2):
+        im = synthetic_chain(5, 200, 360, 3, kind="noise", frame_index=f)[3]
+        assert compare_u8(st.stitch(im), stitcher_ref.stitch_chain(states, labels, im)) == (0, 1.0)
