@@ -306,7 +306,7 @@ def run_ours(args, rank, local_rank, world):
                               "gpu_launches": launches, "clocks": clocks, "e2e": None,
                               "ctas_per_sm": plan.handle.tiled_ctas_per_sm()}), flush=True)
         return
-    pipe = SequencePipeline(st, shapes, device, chunk=args.chunk, depth=3)
+    pipe = SequencePipeline(st, shapes, device, chunk=args.chunk, depth=3, windows=not args.whole_frames)
     host_frames = {l: pinned_like((e2e_batch,) + tuple(images[l].shape)) for l in labels}
     for l in labels:
         for f in range(e2e_batch):
@@ -395,6 +395,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_6x1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="frame-sets per step per GPU (0 = workload default)")
+    ap.add_argument("--whole-frames", action="store_true",
+                    help="e2e path uploads whole camera frames instead of the windows the panorama can see")
     ap.add_argument("--chunk", type=int, default=4, help="frame-sets per pipeline chunk of the e2e path")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--pitch-align", type=int, default=128, help="row pitch alignment of the device-resident panoramas")

@@ -5,6 +5,8 @@ PyTorch is used here only as plumbing - device memory, pinned host memory,
 streams.  All arithmetic happens in the sm_100a kernels behind the C ABI; if
 the library or a CUDA device is missing the calls raise, there is no CPU path.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -50,7 +52,7 @@ class CompiledPlan(object):
             return self.handle.owned_pixels(torch.cuda.current_stream().cuda_stream)
 
     # ---- what the host has to send ------------------------------------------
-    BAND = 64   # source rows per upload band
+    BAND = int(os.environ.get("MCS_UPLOAD_BAND", "64"))   # source rows per upload band
 
     def upload_bands(self, whole=False):
         """Per camera, the byte windows of a frame that can reach the panorama: a list of copies
