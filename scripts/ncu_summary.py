@@ -75,8 +75,9 @@ def main():
         base = op.rstrip(";").split(".")[0]
         n = int(row[sx["Instructions Executed"]])
         s = int(row[sx["# Samples"]] or 0)
-        w = int(row[sx["L1 Wavefronts Shared"]] or 0)
-        wi = int(row[sx["L1 Wavefronts Shared Ideal"]] or 0)
+        # kernels without shared memory have no such columns
+        w = int(row[sx["L1 Wavefronts Shared"]] or 0) if "L1 Wavefronts Shared" in sx else 0
+        wi = int(row[sx["L1 Wavefronts Shared Ideal"]] or 0) if "L1 Wavefronts Shared Ideal" in sx else 0
         ops[base] += n
         samples[base] += s
         total += n
