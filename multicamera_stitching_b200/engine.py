@@ -107,6 +107,23 @@ class CompiledPlan(object):
             raise ValueError("frame pixels must be densely packed (strides %r)" % (st,))
         return t.data_ptr(), pitch, (st[0] if batched else 0)
 
+    def _realigned(self, cam, t, p, pitch, fs, F, batched, stream):
+        h, w = int(t.shape[-3 if self.flat.ndim == 3 else -2]), int(t.shape[-2 if self.flat.ndim == 3 else -1])
+        row = w * self.channels
+        pitch16 = _round_up(row, 16)
+        scratch = self.__dict__.setdefault("_scratch", {})
+        buf = scratch.get(cam)
+        if buf is None or buf.shape[0] < F or buf.shape[1:] != (h, pitch16) or buf.device != t.device:
+            buf = torch.zeros((F, h, pitch16), dtype=torch.uint8, device=t.device)
+            scratch[cam] = buf
+        if batched and F > 1 and fs % pitch:
+            raise ValueError("camera %d: frame stride %d is not a multiple of the row pitch %d" % (cam, fs, pitch))
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream() if stream is None else stream
+            _cabi.copy_window_u8(buf.data_ptr(), pitch16, h * pitch16, p, pitch, fs if batched and F > 1 else h * pitch,
+                                 0, row, 0, h, F, s.cuda_stream)
+        return buf.data_ptr(), pitch16, h * pitch16
+
     def new_output(self, n_frames=None, pitch_align=1):
         """Uninitialised output tensor (every byte of it is written by the
         kernel).  With ``pitch_align`` > 1 rows are padded and a strided view
@@ -132,12 +149,18 @@ class CompiledPlan(object):
         if tuple(out.shape) != self.out_shape(n_frames):
             raise ValueError("output shape %r != %r" % (tuple(out.shape), self.out_shape(n_frames)))
         ptrs, pitches, fstrides = [], [], []
+        tiled = self.handle.tiled_status() == ""
         for l in self.flat.layers:
             t = frames_by_cam[l.cam]
             want = ((F,) if batched else ()) + tuple(l.src_hw) + ((self.channels,) if self.flat.ndim == 3 else ())
             if tuple(t.shape) != want:
                 raise ValueError("camera %d: frame shape %r != %r" % (l.cam, tuple(t.shape), want))
             p, pitch, fs = self._describe(t, batched)
+            if tiled and (p % 16 or pitch % 16 or (batched and F > 1 and fs % 16)):
+                # The TMA-staged kernel needs 16-byte aligned rows; the gather kernel that would
+                # serve this layout is ~5x slower, so the frames take one extra device-side pass
+                # into a pitched scratch buffer (plain cudaMemcpy3DAsync) instead.
+                p, pitch, fs = self._realigned(l.cam, t, p, pitch, fs, F, batched, stream)
             ptrs.append(p)
             pitches.append(pitch)
             fstrides.append(fs)

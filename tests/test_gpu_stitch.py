@@ -306,3 +306,20 @@ def test_batch_equals_single_frames_config2(cuda_device):
         single = st.stitch({l: batch[l][f] for l in labels})
         assert torch.equal(out[f], single)
     _check(out[0].cpu().numpy(), stitcher_ref.stitch_chain(states, labels, sets[0]))
+
+
+def test_rows_that_are_not_16_byte_multiples_still_take_the_tiled_kernel(cuda_device):
+    """360-pixel BGR rows are 1080 bytes: TMA cannot address them, the gather kernel is ~5x slower,
+    so the engine realigns such frames into a pitched scratch buffer (one device-side copy) and
+    launches the tiled kernel."""
+    st, states, labels, images = synthetic_chain(4, 200, 360, 3, kind="noise")
+    ref = stitcher_ref.stitch_chain(states, labels, images)
+    _check(st.stitch(images), ref)
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.tiled_status() == "" and plan.handle.last_variant() == 2
+    sets = [synthetic_chain(4, 200, 360, 3, kind="noise", frame_index=f)[3] for f in range(3)]
+    batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
+    outb = st.stitch_batch(batch)
+    assert plan.handle.last_variant() == 2
+    for f in range(3):
+        _check(outb[f].cpu().numpy(), stitcher_ref.stitch_chain(states, labels, sets[f]))
