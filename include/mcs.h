@@ -195,6 +195,17 @@ int mcs_plan_last_variant(const mcs_plan* plan);
  * instead of switching).  For tests and benchmarks. */
 int mcs_plan_force_variant(mcs_plan* plan, int variant);
 
+/*
+ * Source rows that are not a multiple of 4 bytes (e.g. 854 BGR pixels): the tiled variant addresses
+ * rows as 4-byte words and can serve them only if every source row passed to mcs_stitch_u8 is
+ * followed, inside its pitch, by ZERO bytes up to the next multiple of 4 (they stand in for the
+ * BORDER_CONSTANT 0 taps right of the image).  mcs_plan_rows_need_padding tells whether the plan has
+ * such a layer; mcs_plan_promise_padded_rows records the caller's promise (without it those plans
+ * run the gather variant).
+ */
+int mcs_plan_rows_need_padding(const mcs_plan* plan);
+int mcs_plan_promise_padded_rows(mcs_plan* plan, int promised);
+
 /* "" when the tiled (TMA-staged) variant is available for this plan, else the reason it is
  * not (the gather variant then serves every call). */
 const char* mcs_plan_tiled_status(const mcs_plan* plan);

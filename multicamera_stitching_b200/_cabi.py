@@ -23,7 +23,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_create_maps", "mcs_plan_destroy",
     "mcs_plan_owned_pixels", "mcs_plan_source_windows", "mcs_plan_source_spans", "mcs_copy_window_u8", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_last_variant",
-    "mcs_plan_force_variant",
+    "mcs_plan_force_variant", "mcs_plan_rows_need_padding", "mcs_plan_promise_padded_rows",
     "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_launch_count",
     "mcs_match_hamming_top2", "mcs_ransac_homography", "mcs_resize_linear_u8",
 )
@@ -87,6 +87,10 @@ def load(build_if_missing=False):
     lib.mcs_plan_last_variant.argtypes = [_vp]
     lib.mcs_plan_force_variant.restype = ctypes.c_int
     lib.mcs_plan_force_variant.argtypes = [_vp, ctypes.c_int]
+    lib.mcs_plan_rows_need_padding.restype = ctypes.c_int
+    lib.mcs_plan_rows_need_padding.argtypes = [_vp]
+    lib.mcs_plan_promise_padded_rows.restype = ctypes.c_int
+    lib.mcs_plan_promise_padded_rows.argtypes = [_vp, ctypes.c_int]
     lib.mcs_plan_set_feather.restype = ctypes.c_int
     lib.mcs_plan_set_feather.argtypes = [_vp, ctypes.c_int]
     lib.mcs_plan_tiled_ctas_per_sm.restype = ctypes.c_int
@@ -240,6 +244,12 @@ class Plan(object):
     def force_variant(self, variant):
         """0 = automatic, 1 = gather kernel, 2 = tiled (TMA-staged) kernel."""
         check(_lib.mcs_plan_force_variant(self._h, int(variant)), "mcs_plan_force_variant")
+
+    def rows_need_padding(self):
+        return bool(_lib.mcs_plan_rows_need_padding(self._h))
+
+    def promise_padded_rows(self, promised=True):
+        check(_lib.mcs_plan_promise_padded_rows(self._h, int(bool(promised))), "mcs_plan_promise_padded_rows")
 
     def set_feather(self, feather_log2):
         check(_lib.mcs_plan_set_feather(self._h, int(feather_log2)), "mcs_plan_set_feather")

@@ -105,6 +105,8 @@ struct mcs_plan {
     int force_variant;       // 0 = automatic, 1 = gather, 2 = tiled (diagnostics)
     // tiled variant
     int tiled_ok;            // tile table built and every box within limits
+    int rows_need_pad;       // some source row is not a multiple of 4 bytes: the tiled variant then needs
+    int pad_promised;        // the caller's promise that rows are followed by zero bytes up to one (mcs.h)
     char tiled_why[160];     // why not, when tiled_ok == 0
     int n_tiles;
     int box_bytes;           // shared-memory bytes of one staging buffer (max over layers, 128-aligned)

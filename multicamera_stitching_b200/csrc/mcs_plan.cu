@@ -217,6 +217,15 @@ extern "C" int mcs_plan_destroy(mcs_plan* plan) {
     return MCS_OK;
 }
 
+extern "C" int mcs_plan_rows_need_padding(const mcs_plan* plan) { return plan ? plan->rows_need_pad : 0; }
+
+extern "C" int mcs_plan_promise_padded_rows(mcs_plan* plan, int promised) {
+    MCS_CHECK_ARG(plan != nullptr, "mcs_plan_promise_padded_rows: plan is NULL");
+    plan->pad_promised = promised ? 1 : 0;
+    plan->cache_valid = 0;
+    return MCS_OK;
+}
+
 extern "C" int mcs_plan_source_windows(const mcs_plan* plan, int32_t* xyxy) {
     MCS_CHECK_ARG(plan != nullptr && xyxy != nullptr, "mcs_plan_source_windows: NULL argument");
     // The feather band samples outer cameras inside the pasted rectangles, i.e. outside the

@@ -184,6 +184,7 @@ static int tile_cost(const McsTile& t) {
 
 void mcs_plan_build_tiles(mcs_plan* plan) {
     plan->tiled_ok = 0;
+    plan->rows_need_pad = 0;
     plan->src_win_valid = 0;
     plan->tiled_why[0] = 0;
     const int C = plan->channels;
@@ -198,10 +199,9 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             why(plan, "layer rectangles are not nested (layer %d)", k);
             return;
         }
-        if ((L.src_w * C) % 4 != 0) {
-            why(plan, "layer %d: source row of %d bytes is not a multiple of 4", k, L.src_w * C);
-            return;
-        }
+        // TMA addresses a source row as 4-byte words: a row of another length is served only when
+        // the caller promises zero bytes up to the next multiple of 4 (mcs_plan_promise_padded_rows)
+        if ((L.src_w * C) % 4 != 0) plan->rows_need_pad = 1;
         if (!empty(r)) inner = r;
     }
 

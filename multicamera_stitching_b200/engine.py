@@ -35,6 +35,11 @@ class CompiledPlan(object):
                                      maps=plan_maps(flat))
             if self.feather_log2:
                 self.handle.set_feather(self.feather_log2)
+            # rows that are not a multiple of 4 bytes: run() always passes them through its
+            # zero-padded scratch buffers, which is what the tiled kernel needs to serve them
+            self.pad_rows = self.handle.tiled_status() == "" and self.handle.rows_need_padding()
+            if self.pad_rows:
+                self.handle.promise_padded_rows(True)
         self.cams = [l.cam for l in flat.layers]
         self.out_w, self.out_h, self.channels = flat.out_w, flat.out_h, flat.channels
 
@@ -156,7 +161,7 @@ class CompiledPlan(object):
             if tuple(t.shape) != want:
                 raise ValueError("camera %d: frame shape %r != %r" % (l.cam, tuple(t.shape), want))
             p, pitch, fs = self._describe(t, batched)
-            if tiled and (p % 16 or pitch % 16 or (batched and F > 1 and fs % 16)):
+            if tiled and (self.pad_rows or p % 16 or pitch % 16 or (batched and F > 1 and fs % 16)):
                 # The TMA-staged kernel needs 16-byte aligned rows; the gather kernel that would
                 # serve this layout is ~5x slower, so the frames take one extra device-side pass
                 # into a pitched scratch buffer (plain cudaMemcpy3DAsync) instead.

@@ -323,3 +323,22 @@ def test_rows_that_are_not_16_byte_multiples_still_take_the_tiled_kernel(cuda_de
     assert plan.handle.last_variant() == 2
     for f in range(3):
         _check(outb[f].cpu().numpy(), stitcher_ref.stitch_chain(states, labels, sets[f]))
+
+
+@pytest.mark.parametrize("n,h,w,c", [(3, 120, 131, 3), (2, 97, 403, 1), (4, 90, 854, 3)])
+def test_rows_that_are_not_4_byte_multiples_take_the_tiled_kernel_through_zero_padded_rows(cuda_device, n, h, w, c):
+    """A 131-pixel BGR row is 393 bytes.  The engine's scratch rows are zero-padded, it promises
+    that to the plan (mcs_plan_promise_padded_rows), and the pad bytes stand in for the
+    BORDER_CONSTANT taps right of the image."""
+    st, states, labels, images = synthetic_chain(n, h, w, c, kind="noise")
+    ref = stitcher_ref.stitch_chain(states, labels, images)
+    _check(st.stitch(images), ref)
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.rows_need_padding() and plan.handle.last_variant() == 2
+    dev = {l: torch.from_numpy(images[l]).to(cuda_device) for l in labels}
+    _check(st.stitch(dev).cpu().numpy(), ref)
+    # without the promise the same plan falls back to the gather kernel (direct C-ABI callers)
+    plan.handle.promise_padded_rows(False)
+    _check(st.stitch(dev).cpu().numpy(), ref)
+    assert plan.handle.last_variant() == 1
+    plan.handle.promise_padded_rows(True)
