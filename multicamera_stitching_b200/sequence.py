@@ -74,50 +74,77 @@ class SequencePipeline(object):
         d2h = int(self.slots[0]["dst"][0].numel())
         return h2d, d2h
 
-    def run(self, host_frames, host_out, lo=0, hi=None):
+    def run(self, host_frames, host_out, lo=0, hi=None, ring=False):
         """Composite frames ``[lo, hi)`` of the host sequence into
         ``host_out[lo:hi]``; returns the number of panoramas produced.  The
-        call returns after the last device->host copy has completed."""
+        call returns after the last device->host copy has completed.
+
+        ``ring=True``: the host tensors are rings of ``R`` frame-sets / panoramas and frame ``f``
+        of the sequence lives in slot ``f % R`` (a long synthetic sequence cycled through a few
+        resident frame-sets, or a capture decoded just ahead of the pipeline); ``[lo, hi)`` may
+        then be any range."""
         F = int(host_out.shape[0])
         hi = F if hi is None else hi
+        if ring:
+            return self._run_ring(host_frames, host_out, int(lo), int(hi), F)
         with torch.cuda.device(self.device):
             start = torch.cuda.current_stream()
             for s in (self.s_in, self.s_k, self.s_out):
                 s.wait_stream(start)
             i = 0
             for f0 in range(lo, hi, self.chunk):
-                n = min(self.chunk, hi - f0)
-                slot = self.slots[i % self.depth]
+                self._chunk(i, host_frames, host_out, f0, min(self.chunk, hi - f0))
                 i += 1
-                with torch.cuda.stream(self.s_in):
-                    if slot["used"]:
-                        self.s_in.wait_event(slot["ev_k"])      # previous kernel done reading the slot
-                    for c, label in enumerate(self.labels):
-                        host = host_frames[label]
-                        row, h = self.geometry[c]
-                        copies = self.windows[c]
-                        if len(copies) == 1 and copies[0]["nbytes"] == row and copies[0]["rows"] == h:
-                            slot["src"][c][:n].copy_(host[f0:f0 + n], non_blocking=True)
-                            continue
-                        if copies and not host.is_contiguous():
-                            raise ValueError("host frames of %r must be contiguous" % (label,))
-                        fs = row * h
-                        for w in copies:
-                            _cabi.copy_window_u8(slot["src"][c].data_ptr(), row, fs, host.data_ptr() + f0 * fs, row, fs,
-                                                 w["b0"], w["nbytes"], w["y0"], w["rows"], n, self.s_in.cuda_stream)
-                    slot["ev_in"].record(self.s_in)
-                with torch.cuda.stream(self.s_k):
-                    self.s_k.wait_event(slot["ev_in"])
-                    if slot["used"]:
-                        self.s_k.wait_event(slot["ev_out"])     # previous D2H done reading dst
-                    self.plan.run([t[:n] for t in slot["src"]], out=slot["dst"][:n], n_frames=n,
-                                  stream=self.s_k)
-                    slot["ev_k"].record(self.s_k)
-                with torch.cuda.stream(self.s_out):
-                    self.s_out.wait_event(slot["ev_k"])
-                    host_out[f0:f0 + n].copy_(slot["dst"][:n], non_blocking=True)
-                    slot["ev_out"].record(self.s_out)
-                slot["used"] = True
+            start.wait_stream(self.s_out)
+            start.wait_stream(self.s_k)
+            start.wait_stream(self.s_in)
+        return hi - lo
+
+    def _chunk(self, i, host_frames, host_out, f0, n):
+        """Enqueue chunk ``i``: host frames ``[f0, f0 + n)`` -> slot -> kernel -> ``host_out[f0:f0 + n]``."""
+        slot = self.slots[i % self.depth]
+        with torch.cuda.stream(self.s_in):
+            if slot["used"]:
+                self.s_in.wait_event(slot["ev_k"])      # previous kernel done reading the slot
+            for c, label in enumerate(self.labels):
+                host = host_frames[label]
+                row, h = self.geometry[c]
+                copies = self.windows[c]
+                if len(copies) == 1 and copies[0]["nbytes"] == row and copies[0]["rows"] == h:
+                    slot["src"][c][:n].copy_(host[f0:f0 + n], non_blocking=True)
+                    continue
+                if copies and not host.is_contiguous():
+                    raise ValueError("host frames of %r must be contiguous" % (label,))
+                fs = row * h
+                for w in copies:
+                    _cabi.copy_window_u8(slot["src"][c].data_ptr(), row, fs, host.data_ptr() + f0 * fs, row, fs,
+                                         w["b0"], w["nbytes"], w["y0"], w["rows"], n, self.s_in.cuda_stream)
+            slot["ev_in"].record(self.s_in)
+        with torch.cuda.stream(self.s_k):
+            self.s_k.wait_event(slot["ev_in"])
+            if slot["used"]:
+                self.s_k.wait_event(slot["ev_out"])     # previous D2H done reading dst
+            self.plan.run([t[:n] for t in slot["src"]], out=slot["dst"][:n], n_frames=n,
+                          stream=self.s_k)
+            slot["ev_k"].record(self.s_k)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["ev_k"])
+            host_out[f0:f0 + n].copy_(slot["dst"][:n], non_blocking=True)
+            slot["ev_out"].record(self.s_out)
+        slot["used"] = True
+
+    def _run_ring(self, host_frames, host_out, lo, hi, R):
+        with torch.cuda.device(self.device):
+            start = torch.cuda.current_stream()
+            for s in (self.s_in, self.s_k, self.s_out):
+                s.wait_stream(start)
+            i, f = 0, lo
+            while f < hi:
+                r0 = f % R
+                n = min(self.chunk, hi - f, R - r0)
+                self._chunk(i, host_frames, host_out, r0, n)
+                i += 1
+                f += n
             start.wait_stream(self.s_out)
             start.wait_stream(self.s_k)
             start.wait_stream(self.s_in)

@@ -70,3 +70,21 @@ def test_single_call_numpy_path_uploads_only_the_visible_windows(cuda_device):
     for f in (1, 2):
         im = synthetic_chain(5, 200, 360, 3, kind="noise", frame_index=f)[3]
         assert compare_u8(st.stitch(im), stitcher_ref.stitch_chain(states, labels, im)) == (0, 1.0)
+
+
+def test_ring_mode_cycles_the_host_buffers(cuda_device):
+    """``run(..., ring=True)``: frame f of a long sequence lives in host slot f % R (config 5)."""
+    st, states, labels, images = synthetic_chain(3, 120, 200, 3, kind="noise")
+    shapes = [images[l].shape for l in labels]
+    R = 5
+    sets = [synthetic_chain(3, 120, 200, 3, kind="noise", frame_index=f)[3] for f in range(R)]
+    host = {l: pinned_like((R,) + tuple(images[l].shape)) for l in labels}
+    for l in labels:
+        for f in range(R):
+            host[l][f].copy_(torch.from_numpy(sets[f][l]))
+    pipe = SequencePipeline(st, shapes, cuda_device, chunk=2, depth=2)
+    out = pinned_like((R,) + pipe.plan.out_shape())
+    out.zero_()
+    assert pipe.run(host, out, 3, 3 + 2 * R + 1, ring=True) == 2 * R + 1     # frames 3 .. 13: every slot written
+    for r in range(R):
+        assert compare_u8(out[r].numpy(), stitcher_ref.stitch_chain(states, labels, sets[r])) == (0, 1.0)
