@@ -121,8 +121,6 @@ class CompiledPlan(object):
         if buf is None or buf.shape[0] < F or buf.shape[1:] != (h, pitch16) or buf.device != t.device:
             buf = torch.zeros((F, h, pitch16), dtype=torch.uint8, device=t.device)
             scratch[cam] = buf
-        if batched and F > 1 and fs % pitch:
-            raise ValueError("camera %d: frame stride %d is not a multiple of the row pitch %d" % (cam, fs, pitch))
         with torch.cuda.device(self.device):
             s = torch.cuda.current_stream() if stream is None else stream
             _cabi.copy_window_u8(buf.data_ptr(), pitch16, h * pitch16, p, pitch, fs if batched and F > 1 else h * pitch,

@@ -342,3 +342,22 @@ def test_rows_that_are_not_4_byte_multiples_take_the_tiled_kernel_through_zero_p
     _check(st.stitch(dev).cpu().numpy(), ref)
     assert plan.handle.last_variant() == 1
     plan.handle.promise_padded_rows(True)
+
+
+def test_realigned_sources_with_odd_frame_strides(cuda_device):
+    """Batched views whose frames are not a whole number of rows apart still go through the scratch
+    copy (frame by frame) and the tiled kernel."""
+    st, states, labels, images = synthetic_chain(3, 96, 131, 3, kind="noise")
+    sets = [synthetic_chain(3, 96, 131, 3, kind="noise", frame_index=f)[3] for f in range(3)]
+    batch = {}
+    for l in labels:
+        h, w, c = images[l].shape
+        flat = torch.zeros(3 * (h * w * c + 7) + 5, dtype=torch.uint8, device=cuda_device)
+        view = torch.as_strided(flat, (3, h, w, c), (h * w * c + 7, w * c, c, 1), 5)
+        view.copy_(torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device))
+        batch[l] = view
+    out = st.stitch_batch(batch)
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.last_variant() == 2
+    for f in range(3):
+        _check(out[f].cpu().numpy(), stitcher_ref.stitch_chain(states, labels, sets[f]))
