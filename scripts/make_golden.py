@@ -13,6 +13,10 @@
                         (oracle/stitcher_ref.py driving cv2), with its geometry (:293-351)
   match_cv2.npz         cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) + the ratio loop of :428-433
                         on seeded descriptors with planted partners and exact ties
+  resize_cv2.npz        cv2.resize(INTER_LINEAR) as StitcherClass.py:229 / :233 call it (up, down, exact 2 x 2
+                        decimation, one axis halved, identity, a transposed one-channel plane)
+  prewarp_cv2.npz       cv2.undistort + cv2.warpPerspective as the callers run them in front of the stitcher
+                        (view.py:378-388), extrinsic matrix from the reference's own CalculateProjectionMatrix
 All inputs are regenerated from seeds by the tests; only the expected outputs (and the
 descriptor sets) are stored.
 """
@@ -120,6 +124,45 @@ def golden_match():
     np.savez_compressed(os.path.join(OUT, "match_cv2.npz"), fa=fa, fb=fb, idx=idx, dist=dist, matches=matches)
 
 
+RESIZE_CASES = {"up": (101, 77), "down": (40, 23), "half_area": (41, 30), "identity": (82, 60), "one_axis": (41, 90)}
+
+
+def resize_source():
+    # 60 x 82 so that (41, 30) is an exact 2 x 2 decimation (OpenCV's area kernel)
+    return np.random.default_rng(4321).integers(0, 256, size=(60, 82, 3), dtype=np.uint8)
+
+
+def golden_resize():
+    """cv2.resize(INTER_LINEAR) as StitcherClass.py:229 / :233 call it."""
+    src = resize_source()
+    out = {}
+    for name, dsize in RESIZE_CASES.items():
+        out[name] = cv2.resize(src, dsize, interpolation=cv2.INTER_LINEAR)
+    out["plane"] = cv2.resize(np.ascontiguousarray(src[:, :, 0].T), (60, 82), interpolation=cv2.INTER_LINEAR)
+    np.savez_compressed(os.path.join(OUT, "resize_cv2.npz"), **out)
+
+
+PREWARP_CAMERA = dict(mtx=[[130.0, 0.0, 84.3], [0.0, 131.5, 47.9], [0.0, 0.0, 1.0]],
+                      dist=[-0.32, 0.12, 0.001, -0.0007, -0.02])
+PREWARP_QUAD = ([(40, 45), (130, 45), (155, 85), (10, 85)], [(0, 0), (120, 0), (120, 80), (0, 80)])
+
+
+def prewarp_source():
+    return np.random.default_rng(2468).integers(0, 256, size=(96, 168, 3), dtype=np.uint8)
+
+
+def golden_prewarp(ref_root):
+    """cv2.undistort + cv2.warpPerspective as the callers run them (view.py:378-388), with the
+    extrinsic matrix from the REFERENCE'S OWN Utils.CalculateProjectionMatrix (Extrinsic.py:96-99)."""
+    U = load_reference_utils(ref_root)
+    src = prewarp_source()
+    mtx, dist = np.array(PREWARP_CAMERA["mtx"]), np.array(PREWARP_CAMERA["dist"])
+    M, _ = U.CalculateProjectionMatrix(src_pts=PREWARP_QUAD[0], dst_pts=PREWARP_QUAD[1])
+    und = cv2.undistort(src=src, cameraMatrix=mtx, distCoeffs=dist)
+    bird = cv2.warpPerspective(src=und, M=M, dsize=(120, 80))
+    np.savez_compressed(os.path.join(OUT, "prewarp_cv2.npz"), undistorted=und, birdseye=bird, M=M)
+
+
 def recorded_csv_text():
     """A small, well-formed data.csv in the capture node's format (two captures, three cameras)."""
     rows = [["capture_id", "timestamp", "camera_label", "image_file"]]
@@ -159,6 +202,8 @@ if __name__ == "__main__":
     golden_warp()
     golden_chain()
     golden_match()
+    golden_resize()
+    golden_prewarp(ref_root)
     golden_recorded(ref_root)
     with open(os.path.join(OUT, "README.md"), "w") as f:
         f.write("Fixtures written by scripts/make_golden.py (cv2 %s, numpy %s).\n"

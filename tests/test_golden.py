@@ -75,7 +75,61 @@ def test_match_model_reproduces_bfmatcher_golden():
     assert np.array_equal(fa, g["fa"]) and np.array_equal(fb, g["fb"])   # the seeds still give these sets
 
 
+def test_resize_model_reproduces_cv2_golden():
+    from oracle.resize_model import resize_linear_u8
+    mg = _gen()
+    g = load("resize_cv2.npz")
+    src = mg.resize_source()
+    for name, dsize in mg.RESIZE_CASES.items():
+        assert np.array_equal(resize_linear_u8(src, dsize), g[name]), name
+    assert np.array_equal(resize_linear_u8(np.ascontiguousarray(src[:, :, 0].T), (60, 82)), g["plane"])
+
+
+def test_prewarp_oracle_reproduces_cv2_golden():
+    from multicamera_stitching_b200 import CalculateProjectionMatrix, prewarp
+    from oracle import prewarp_ref
+    mg = _gen()
+    g = load("prewarp_cv2.npz")
+    src = mg.prewarp_source()
+    mtx, dist = np.array(mg.PREWARP_CAMERA["mtx"]), np.array(mg.PREWARP_CAMERA["dist"])
+    M, _ = CalculateProjectionMatrix(src_pts=mg.PREWARP_QUAD[0], dst_pts=mg.PREWARP_QUAD[1])
+    assert np.array_equal(M, g["M"])                      # our Utils mirror = the reference's own module
+    maps = prewarp.undistort_maps(mtx, dist, (src.shape[1], src.shape[0]))
+    und = prewarp_ref.remap_fixed_point(src, *maps)
+    assert np.array_equal(und, g["undistorted"])
+    assert np.array_equal(warp_model.warp_perspective_u8(und, M, (120, 80)), g["birdseye"])
+    ic, ec = {"mtx": mtx, "dist": dist}, {"M": M, "dst_size": (120, 80)}
+    assert np.array_equal(prewarp_ref.prewarp(src, ic, ec), g["birdseye"])
+
+
 # ---- GPU ---------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_resize_equals_golden(cuda_device):
+    import torch
+    from multicamera_stitching_b200.engine import CompositeEngine
+    mg = _gen()
+    g = load("resize_cv2.npz")
+    src = torch.from_numpy(mg.resize_source()).to(cuda_device)
+    eng = CompositeEngine()
+    for name, dsize in mg.RESIZE_CASES.items():
+        assert np.array_equal(eng.resize(src, (dsize[1], dsize[0])).cpu().numpy(), g[name]), name
+    plane = src[:, :, 0].T.contiguous()
+    assert np.array_equal(eng.resize(plane, (82, 60)).cpu().numpy(), g["plane"])
+
+
+@pytest.mark.gpu
+def test_gpu_prewarp_equals_golden(cuda_device):
+    from multicamera_stitching_b200 import prewarp
+    mg = _gen()
+    g = load("prewarp_cv2.npz")
+    src = mg.prewarp_source()
+    pw = prewarp.PreWarp({"mtx": np.array(mg.PREWARP_CAMERA["mtx"]), "dist": np.array(mg.PREWARP_CAMERA["dist"])},
+                         {"M": g["M"], "dst_size": (120, 80)})
+    assert np.array_equal(pw.undistort(src), g["undistorted"])
+    assert np.array_equal(pw(src), g["birdseye"])
+
+
+
 @pytest.mark.gpu
 def test_gpu_chain_equals_golden_panorama(cuda_device):
     from helpers import synthetic_chain
