@@ -9,7 +9,11 @@ only its own output goes back to the host (SURVEY.md section 8 row e).
 """
 import torch
 
+import os
+
 from . import _cabi
+
+_NO_KERNEL = bool(os.environ.get("MCS_SEQ_NO_KERNEL"))   # experiments: copies only (wrong panoramas)
 
 
 def shard_range(n_frames, world_size, rank):
@@ -124,8 +128,9 @@ class SequencePipeline(object):
             self.s_k.wait_event(slot["ev_in"])
             if slot["used"]:
                 self.s_k.wait_event(slot["ev_out"])     # previous D2H done reading dst
-            self.plan.run([t[:n] for t in slot["src"]], out=slot["dst"][:n], n_frames=n,
-                          stream=self.s_k)
+            if not _NO_KERNEL:
+                self.plan.run([t[:n] for t in slot["src"]], out=slot["dst"][:n], n_frames=n,
+                              stream=self.s_k)
             slot["ev_k"].record(self.s_k)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["ev_k"])

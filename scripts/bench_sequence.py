@@ -33,7 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=10000)
     ap.add_argument("--ring", type=int, default=32)
-    ap.add_argument("--chunk", type=int, default=4)
+    ap.add_argument("--chunk", type=int, default=16)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
