@@ -233,48 +233,3 @@ extern "C" int mcs_resize_linear_u8(const uint8_t* src, int src_w, int src_h, in
     MCS_CHECK_CUDA(cudaGetLastError());
     return MCS_OK;
 }
-
-// ---------------------------------------------------------------------------------------------
-// Window upload by the SMs: the copy engine moves a strided window (rows of a few KB out of a wider
-// pitch) at ~77 % of what it reaches on contiguous memory; threads reading mapped pinned host
-// memory with 16-byte loads do not care about the stride.  Same contract as mcs_copy_window_u8
-// for a host -> device copy with 16-byte aligned rows (x_byte0, width, pitches, bases).
-__global__ void __launch_bounds__(256)
-mcs_upload_window_kernel(uint8_t* __restrict__ dst, long long dst_pitch, long long dst_fs,
-                         const uint8_t* __restrict__ src, long long src_pitch, long long src_fs, long long x_byte0,
-                         int chunks_per_row, int y0, int rows, int n_frames) {
-    const long long total = (long long)chunks_per_row * rows * n_frames;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % chunks_per_row);
-        const long long rf = i / chunks_per_row;
-        const int r = (int)(rf % rows);
-        const long long f = rf / rows;
-        const long long off = x_byte0 + 16ll * c;
-        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src + f * src_fs + (long long)(y0 + r) * src_pitch + off));
-        *reinterpret_cast<uint4*>(dst + f * dst_fs + (long long)(y0 + r) * dst_pitch + off) = v;
-    }
-}
-
-extern "C" int mcs_upload_window_u8(void* dst, int64_t dst_pitch_bytes, int64_t dst_frame_stride, const void* src_host,
-                                    int64_t src_pitch_bytes, int64_t src_frame_stride, int64_t x_byte0,
-                                    int64_t width_bytes, int y0, int rows, int n_frames, int n_ctas,
-                                    void* cuda_stream) {
-    MCS_CHECK_ARG(dst != nullptr && src_host != nullptr, "mcs_upload_window_u8: NULL buffer");
-    MCS_CHECK_ARG(x_byte0 >= 0 && width_bytes >= 0 && y0 >= 0 && rows >= 0 && n_frames >= 0,
-                  "mcs_upload_window_u8: negative extent");
-    if (width_bytes == 0 || rows == 0 || n_frames == 0) return MCS_OK;
-    const bool aligned = ((x_byte0 | width_bytes | dst_pitch_bytes | src_pitch_bytes | dst_frame_stride | src_frame_stride) & 15) == 0 &&
-                         ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src_host)) & 15) == 0;
-    MCS_CHECK_ARG(aligned, "mcs_upload_window_u8: window, pitches and bases must be multiples of 16 bytes");
-    // the host buffer must be pinned and mapped (cudaHostAlloc / cudaHostRegister under unified addressing)
-    void* dev_src = nullptr;
-    MCS_CHECK_CUDA(cudaHostGetDevicePointer(&dev_src, const_cast<void*>(src_host), 0));
-    const int ctas = n_ctas > 0 ? n_ctas : 64;
-    mcs_upload_window_kernel<<<ctas, 256, 0, (cudaStream_t)cuda_stream>>>(
-        static_cast<uint8_t*>(dst), dst_pitch_bytes, dst_frame_stride, static_cast<const uint8_t*>(dev_src),
-        src_pitch_bytes, src_frame_stride, x_byte0, (int)(width_bytes / 16), y0, rows, n_frames);
-    mcs_count_launch(1);
-    MCS_CHECK_CUDA(cudaGetLastError());
-    return MCS_OK;
-}
