@@ -157,7 +157,7 @@ def write_capture(path, frame_sets, capture_id=0, timestamps=None, quality=80, i
     return stamps
 
 
-def stitch_capture(stitcher, seq, capture=0, lo=0, hi=None, device=None, chunk=4, depth=3, batch=32,
+def stitch_capture(stitcher, seq, capture=0, lo=0, hi=None, device=None, chunk=16, depth=3, batch=32,
                    rank=0, world_size=1, workers=None):
     """Composite frame-sets ``[lo, hi)`` of a capture (this rank's share of them) and return
     ``(first_frame, panoramas)`` with ``panoramas`` a host uint8 tensor ``[n, H_out, W_out, C]``."""

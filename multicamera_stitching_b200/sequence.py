@@ -39,7 +39,7 @@ class SequencePipeline(object):
     tensor ``[F, H, W, C]``, ``host_out`` a pinned ``[F, H_out, W_out, C]``.
     """
 
-    def __init__(self, stitcher, img_shapes, device, chunk=4, depth=2, windows=True):
+    def __init__(self, stitcher, img_shapes, device, chunk=16, depth=3, windows=True):
         self.stitcher = stitcher
         self.device = torch.device(device)
         self.labels = list(stitcher.img_labels)
