@@ -26,6 +26,20 @@ def shard_range(n_frames, world_size, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def ring_chunks(lo, hi, ring, chunk):
+    """How frames ``[lo, hi)`` of a sequence held in a ring of ``ring`` host slots (frame ``f`` in slot
+    ``f % ring``) are cut into pipeline chunks: ``(slot, n)`` pairs of at most ``chunk`` consecutive
+    slots that never wrap around the end of the ring."""
+    out = []
+    f = int(lo)
+    while f < hi:
+        r0 = f % ring
+        n = min(int(chunk), hi - f, ring - r0)
+        out.append((r0, n))
+        f += n
+    return out
+
+
 def pinned_like(shape, dtype=torch.uint8):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
 
@@ -143,13 +157,8 @@ class SequencePipeline(object):
             start = torch.cuda.current_stream()
             for s in (self.s_in, self.s_k, self.s_out):
                 s.wait_stream(start)
-            i, f = 0, lo
-            while f < hi:
-                r0 = f % R
-                n = min(self.chunk, hi - f, R - r0)
+            for i, (r0, n) in enumerate(ring_chunks(lo, hi, R, self.chunk)):
                 self._chunk(i, host_frames, host_out, r0, n)
-                i += 1
-                f += n
             start.wait_stream(self.s_out)
             start.wait_stream(self.s_k)
             start.wait_stream(self.s_in)

@@ -10,7 +10,7 @@ import pytest
 import torch
 import torch.multiprocessing as mp
 
-from multicamera_stitching_b200.sequence import shard_range
+from multicamera_stitching_b200.sequence import ring_chunks, shard_range
 
 
 def test_shard_ranges_tile_the_sequence():
@@ -94,3 +94,21 @@ def test_single_rank_context_needs_no_process_group():
     ctx.barrier()
     assert ctx.max_over_ranks(3.5) == 3.5 and ctx.sum_over_ranks(2) == 2.0
     assert ctx.gather_frame_summaries(0, [1, 2, 3]).tolist() == [1, 2, 3]
+
+
+def test_ring_chunks_cover_the_range_without_wrapping():
+    """Config 5 cycles a long sequence through a ring of host slots: the chunks of any frame range
+    cover it exactly once, in order, and never run past the end of the ring."""
+    for lo, hi, ring, chunk in ((0, 100, 32, 16), (3, 14, 5, 2), (1250, 2500, 32, 16), (7, 8, 4, 16), (0, 0, 8, 4)):
+        chunks = ring_chunks(lo, hi, ring, chunk)
+        assert sum(n for _, n in chunks) == hi - lo
+        f = lo
+        for slot, n in chunks:
+            assert slot == f % ring and 1 <= n <= chunk and slot + n <= ring
+            f += n
+    # the shards of a 10 000-frame sequence over 8 ranks tile it, and so do their chunks
+    total = 0
+    for rank in range(8):
+        a, b = shard_range(10000, 8, rank)
+        total += sum(n for _, n in ring_chunks(a, b, 32, 16))
+    assert total == 10000
