@@ -304,7 +304,8 @@ def run_ours(args, rank, local_rank, world):
             print(json.dumps({"metric": "panoramas_per_sec", "value": pps, "ms_per_step": ms_step,
                               "roofline": {"achieved": achieved, "frac": achieved / peak}, "parity": parity,
                               "gpu_launches": launches, "clocks": clocks, "e2e": None,
-                              "ctas_per_sm": plan.handle.tiled_ctas_per_sm()}), flush=True)
+                              "ctas_per_sm": plan.handle.tiled_ctas_per_sm(),
+                              "tiled": plan.handle.tiled_stats()}), flush=True)
         return
     pipe = SequencePipeline(st, shapes, device, chunk=args.chunk, depth=3, windows=not args.whole_frames)
     host_frames = {l: pinned_like((e2e_batch,) + tuple(images[l].shape)) for l in labels}

@@ -214,6 +214,11 @@ const char* mcs_plan_tiled_status(const mcs_plan* plan);
  * tiled launch); the persistent grid is this times the SM count.  Diagnostics. */
 int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan);
 
+/* Shape of the tiled variant's work table (diagnostics; host int32 out[8]): tiles in total, FAST
+ * (four-pixel group descriptors), WARP (per-pixel descriptors), COPY and ZERO tiles, general
+ * passes per FAST tile, bytes of one staged source box, frames per sweep of the table. */
+int mcs_plan_tiled_stats(const mcs_plan* plan, int32_t* out);
+
 /*
  * mcs_resize_linear_u8 - cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR) for
  * n_frames uint8 images, bit-exact with OpenCV's 8-bit linear resize (11-bit coefficients,

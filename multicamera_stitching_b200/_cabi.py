@@ -24,7 +24,7 @@ EXPORTS = (
     "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_create_maps", "mcs_plan_destroy",
     "mcs_plan_owned_pixels", "mcs_plan_source_windows", "mcs_plan_source_spans", "mcs_copy_window_u8", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_last_variant",
     "mcs_plan_force_variant", "mcs_plan_rows_need_padding", "mcs_plan_promise_padded_rows",
-    "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_launch_count",
+    "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_plan_tiled_stats", "mcs_launch_count",
     "mcs_match_hamming_top2", "mcs_ransac_homography", "mcs_resize_linear_u8",
 )
 
@@ -97,6 +97,8 @@ def load(build_if_missing=False):
     lib.mcs_plan_tiled_ctas_per_sm.argtypes = [_vp]
     lib.mcs_plan_tiled_status.restype = ctypes.c_char_p
     lib.mcs_plan_tiled_status.argtypes = [_vp]
+    lib.mcs_plan_tiled_stats.restype = ctypes.c_int
+    lib.mcs_plan_tiled_stats.argtypes = [_vp, _c_i32p]
     lib.mcs_launch_count.restype = ctypes.c_int64
     lib.mcs_launch_count.argtypes = []
     lib.mcs_match_hamming_top2.restype = ctypes.c_int
@@ -256,6 +258,13 @@ class Plan(object):
 
     def tiled_ctas_per_sm(self):
         return int(_lib.mcs_plan_tiled_ctas_per_sm(self._h))
+
+    def tiled_stats(self):
+        """Work table of the tiled variant: tile counts per class, general passes, box bytes, frame block."""
+        out = np.zeros(8, np.int32)
+        check(_lib.mcs_plan_tiled_stats(self._h, out.ctypes.data_as(_c_i32p)), "mcs_plan_tiled_stats")
+        keys = ("tiles", "fast", "warp", "copy", "zero", "fast_passes", "box_bytes", "frame_block")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def tiled_status(self):
         """'' when the tiled variant is available, else why it is not."""

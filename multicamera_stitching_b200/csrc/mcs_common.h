@@ -74,7 +74,18 @@ static_assert(sizeof(McsTile) == 32, "McsTile must stay 32 bytes");
 
 #define MCS_TILE_ZERO 0   // nothing to sample: write zeros
 #define MCS_TILE_COPY 1   // verbatim paste of the source window
-#define MCS_TILE_WARP 2   // fixed-point bilinear resample from the staged source box
+#define MCS_TILE_WARP 2   // fixed-point bilinear resample from the staged source box, one descriptor per pixel
+#define MCS_TILE_FAST 3   // the same resample through the group descriptors (four adjacent pixels per thread share
+                          // one source window; pixels that do not fit that template go through a short per-pixel list)
+#define MCS_N_CLASSES 4
+
+// Group ("fast") descriptors of a WARP tile, C == 3 only (mcs_tiles.cu builds them, mcs_stitch_tiled.cu reads them).
+// One record per tile: [McsTile, 32 B][general-list length of each warp, 8 x u8][pad to 64 B]
+// [group descriptors 2 slots x 8 warps x 32 lanes x uint2][general list: passes x 8 warps x 32 lanes x uint2].
+#define MCS_FAST_HEADER_BYTES 64
+#define MCS_FAST_GROUP_BYTES (2 * MCS_TILED_WARPS * 32 * 8)
+#define MCS_FAST_PASS_BYTES (MCS_TILED_WARPS * 32 * 8)
+#define MCS_FAST_MAX_PASSES 2
 
 // gather-variant launch geometry (64 x 16 pixel blocks)
 #define MCS_TILE_W 64
@@ -111,9 +122,13 @@ struct mcs_plan {
     int n_tiles;
     int box_bytes;           // shared-memory bytes of one staging buffer (max over layers, 128-aligned)
     McsTile* d_tiles;
+    int4* d_issue;           // per tile {layer, bx, by, staged box bytes}: what the box issuer of the tiled kernel reads
     McsLayer* d_layers;
     int2* d_maps[MCS_MAX_LAYERS];   // coordinate maps of the REMAP layers (owned by the plan)
     uint32_t* d_desc;        // per-pixel descriptors of the WARP tiles, 2048 words per tile (mcs_tiles.cu)
+    uint8_t* d_fast;         // group-descriptor records of the FAST tiles (they come first in the table), or nullptr
+    int fast_stride;         // bytes per record: header + groups + fast_passes general passes
+    int fast_passes;         // general passes every record carries (max over the FAST tiles, 0..MCS_FAST_MAX_PASSES)
     int src_win[MCS_MAX_LAYERS][4];   // per layer: source window {x0, y0, x1, y1} its owned pixels read
     int src_win_valid;       // set with the tile table; otherwise the whole frame counts
     int* h_row_span[MCS_MAX_LAYERS];   // host, per source row {x0, x1} of the pixels read (nullptr = unknown)
@@ -131,8 +146,9 @@ struct mcs_plan {
     // one contiguous range of equal estimated cost per CTA; h_cum[t] = summed per-frame cost of
     // tiles 0..t-1.  The cut positions depend on (n_frames, grid) and are cached in a few slots.
     long long* h_cum;        // host, n_tiles + 1 entries
-    int class_first[4];      // the tile table is sorted WARP, COPY, ZERO: first tile of each class, then n_tiles
-    int2* d_sched;           // device, MCS_SCHED_SLOTS x 3 x (MCS_SCHED_MAX_GRID + 1) entries {tile, frame}
+    int class_first[MCS_N_CLASSES + 1];   // the tile table is sorted FAST, WARP, COPY, ZERO: first tile of each
+                             // class, then n_tiles
+    int2* d_sched;           // device, MCS_SCHED_SLOTS x MCS_N_CLASSES x (MCS_SCHED_MAX_GRID + 1) entries {tile, frame}
     int sched_frames[MCS_SCHED_SLOTS];
     int sched_grid[MCS_SCHED_SLOTS];
     int sched_next;          // slot overwritten next

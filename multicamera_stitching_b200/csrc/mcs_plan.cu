@@ -311,6 +311,18 @@ extern "C" const char* mcs_plan_tiled_status(const mcs_plan* plan) {
 
 extern "C" int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan) { return plan ? plan->grid_ctas_per_sm : 0; }
 
+extern "C" int mcs_plan_tiled_stats(const mcs_plan* plan, int32_t* out) {
+    MCS_CHECK_ARG(plan != nullptr && out != nullptr, "mcs_plan_tiled_stats: NULL argument");
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!plan->tiled_ok) return MCS_OK;
+    out[0] = plan->n_tiles;
+    for (int c = 0; c < MCS_N_CLASSES; ++c) out[1 + c] = plan->class_first[c + 1] - plan->class_first[c];
+    out[5] = plan->fast_passes;
+    out[6] = plan->box_bytes;
+    out[7] = plan->frame_block;
+    return MCS_OK;
+}
+
 static void free_strips(mcs_plan* plan) {
     mcs_feather_free_table(plan);
     if (plan->d_strips) cudaFree(plan->d_strips);

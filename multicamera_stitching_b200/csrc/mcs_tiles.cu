@@ -101,6 +101,98 @@ mcs_tile_desc_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restri
     }
 }
 
+// Group descriptors of a WARP tile (C == 3): thread (warp, lane) describes, for each of its two cell
+// rows (slot 0: row warp, slot 1: row warp + 8), the GROUP of four adjacent pixels at cell columns
+// 4 lane .. 4 lane + 3.  At near-unit scale those pixels sample adjacent source pixels of one source
+// row pair, so one window of five words per source row serves all four of them.  The template: pixel
+// j's taps start 3 j bytes after those of the group's anchor (bA = box byte offset of the first owned
+// pixel's tap, minus 3 bytes per preceding column).  A group record is
+//   x = bA | ax0 << 16 | ay0 << 21,   y = ax1 | ay1 << 5 | ax2 << 10 | ay2 << 15 | ax3 << 20 | ay3 << 25
+// Owned pixels that do not fit the template (the source column or row slips inside the group) go to
+// the warp's GENERAL list, one entry per pixel: x = the per-pixel descriptor of mcs_tile_desc_kernel,
+// y = slot << 7 | cell column (0xffffffff = unused entry).  The list is stored pass-major
+// ([pass][warp][lane]) so that lane l of the warp resamples entries l, 32 + l, ...
+// `counts` (analysis, may be nullptr) receives the list length of each warp, saturated at 255; records
+// are written when `rec` is not nullptr (entries beyond passes * 32 are dropped: the host only marks
+// a tile FAST when every warp's list fits).
+__global__ void __launch_bounds__(256)
+mcs_tile_fast_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restrict__ layers, int n_tiles,
+                     uint8_t* __restrict__ rec, int stride, int passes, uint8_t* __restrict__ counts) {
+    const int t = blockIdx.x;
+    if (t >= n_tiles) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const McsTile tile = tiles[t];
+    const McsLayer& L = layers[tile.layer];
+    const int sp = L.bw4 * 4;
+    uint2 grp[2];
+    uint2 gen[8];
+    int n_gen = 0;
+#pragma unroll
+    for (int slot = 0; slot < 2; ++slot) {
+        const int row = warp + 8 * slot;
+        int b[4], ax[4], ay[4];
+        bool own[4];
+        int j0 = 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = 4 * lane + j;
+            own[j] = col >= tile.c0 && col < tile.c1 && row < tile.h;
+            b[j] = ax[j] = ay[j] = 0;
+            if (own[j]) {
+                const int xl = tile.cx0 + col - L.ox, yl = tile.y0 + row - L.oy;
+                int X, Y;
+                layer_coords(L, xl, yl, X, Y);
+                const int sx = max(-2, min(L.src_w, sat16(X >> 5))), sy = max(-2, min(L.src_h, sat16(Y >> 5)));
+                b[j] = (sy - tile.by) * sp + sx * 3 - 4 * tile.bx;
+                ax[j] = X & 31;
+                ay[j] = Y & 31;
+                if (j0 == 4) j0 = j;
+            }
+        }
+        int bA = j0 < 4 ? b[j0] - 3 * j0 : 0;
+        const bool anchored = bA >= 0;   // an anchor left of the box start is not addressable
+        if (!anchored) bA = 0;
+        uint32_t fx = (uint32_t)bA, fy = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool fit = own[j] && anchored && b[j] == bA + 3 * j;
+            if (fit) {
+                if (j == 0) fx |= ((uint32_t)ax[0] << 16) | ((uint32_t)ay[0] << 21);
+                else fy |= (((uint32_t)ax[j]) | ((uint32_t)ay[j] << 5)) << (10 * (j - 1));
+            } else if (own[j]) {
+                gen[n_gen++] = make_uint2((uint32_t)b[j] | ((uint32_t)ax[j] << 16) | ((uint32_t)ay[j] << 21),
+                                          (uint32_t)(slot << 7) | (uint32_t)(4 * lane + j));
+            }
+        }
+        grp[slot] = make_uint2(fx, fy);
+    }
+    // position of this lane's entries in the warp's list
+    int incl = n_gen;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int first = incl - n_gen;
+    if (counts && lane == 0) counts[(size_t)t * 8 + warp] = (uint8_t)min(total, 255);
+    if (!rec) return;
+    uint8_t* r = rec + (size_t)t * stride;
+    if (threadIdx.x < 8) reinterpret_cast<int*>(r)[threadIdx.x] = reinterpret_cast<const int*>(&tiles[t])[threadIdx.x];
+    if (lane == 0) r[32 + warp] = (uint8_t)min(total, 255);
+    uint2* g = reinterpret_cast<uint2*>(r + MCS_FAST_HEADER_BYTES);
+    g[(0 * 8 + warp) * 32 + lane] = grp[0];
+    g[(1 * 8 + warp) * 32 + lane] = grp[1];
+    uint2* lst = reinterpret_cast<uint2*>(r + MCS_FAST_HEADER_BYTES + MCS_FAST_GROUP_BYTES);
+    for (int p = 0; p < passes; ++p) lst[(p * 8 + warp) * 32 + lane] = make_uint2(0u, 0xffffffffu);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = first + i;
+        if (i < n_gen && e < passes * 32) lst[((e >> 5) * 8 + warp) * 32 + (e & 31)] = gen[i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -154,9 +246,13 @@ void why(mcs_plan* plan, const char* fmt, ...) {
 void mcs_plan_free_tiles(mcs_plan* plan) {
     if (plan->d_tiles) cudaFree(plan->d_tiles);
     if (plan->d_layers) cudaFree(plan->d_layers);
+    if (plan->d_issue) cudaFree(plan->d_issue);
+    plan->d_issue = nullptr;
     if (plan->d_sched) cudaFree(plan->d_sched);
     if (plan->d_desc) cudaFree(plan->d_desc);
+    if (plan->d_fast) cudaFree(plan->d_fast);
     plan->d_desc = nullptr;
+    plan->d_fast = nullptr;
     free(plan->h_cum);
     for (int k = 0; k < MCS_MAX_LAYERS; ++k) {
         free(plan->h_row_span[k]);
@@ -172,9 +268,10 @@ void mcs_plan_free_tiles(mcs_plan* plan) {
 
 // Estimated cost of one frame of a tile, in consumer-warp instructions of the tiled kernel: the
 // slowest warp sets the pace of a cell (all warps share the staged box).
-static int tile_cost(const McsTile& t) {
+static int tile_cost(const McsTile& t, int fast_passes) {
     if (t.cls == MCS_TILE_ZERO) return 40;
     if (t.cls == MCS_TILE_COPY) return 90;
+    if (t.cls == MCS_TILE_FAST) return 70 + 72 * (t.h > MCS_TILED_WARPS ? 2 : 1) + 36 * fast_passes;
     int groups = 0;
     for (int g = 0; g < 4; ++g)
         if (32 * g < t.c1 && 32 * g + 32 > t.c0) ++groups;
@@ -323,7 +420,20 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         if (tiles[i].layer >= 0) tiles[i].reserved = bw4[tiles[i].layer] * 4 * bh[tiles[i].layer];
     // Work split: tiles grouped by class (each class keeps its layer / row / column order, so a
     // CTA's range covers neighbouring cells), costs prefix-summed for the launch-time cut.
-    std::stable_sort(tiles.begin(), tiles.end(), [](const McsTile& a, const McsTile& b) { return a.cls > b.cls; });
+    // Inside a class the tiles run in bands of $MCS_TILED_ORDER cell rows over the whole panorama width; inside a band
+    // layer by layer, each layer's cells in raster order (0 = no bands: layer by layer).
+    const char* env_order = getenv("MCS_TILED_ORDER");
+    const int band = env_order ? atoi(env_order) : 1;
+    auto by_class = [band](const McsTile& a, const McsTile& b) {
+        if (a.cls != b.cls) return a.cls > b.cls;
+        if (band <= 0) return false;
+        const int ba = a.y0 / (MCS_CELL_H * band), bb = b.y0 / (MCS_CELL_H * band);
+        if (ba != bb) return ba < bb;
+        if (band > 1 && a.layer != b.layer) return a.layer < b.layer;
+        if (a.y0 / MCS_CELL_H != b.y0 / MCS_CELL_H) return a.y0 < b.y0;
+        return a.cx0 < b.cx0;
+    };
+    std::stable_sort(tiles.begin(), tiles.end(), by_class);
     long long* h_cum = static_cast<long long*>(malloc(sizeof(long long) * (n_tiles + 1)));
     int2* d_sched = nullptr;
     if (!h_cum) {
@@ -332,31 +442,97 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         cudaFree(d_layers);
         return;
     }
+    e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_layers, plan->layers, sizeof(McsLayer) * MCS_MAX_LAYERS, cudaMemcpyHostToDevice);
+
+    // FAST class (C == 3): WARP tiles whose pixels fit the four-pixel group template but for a short
+    // per-warp list.  Analysis pass first (list lengths only), then the records once the table has
+    // its final order.
+    int n_warp_tiles = 0;
+    while (n_warp_tiles < n_tiles && tiles[n_warp_tiles].cls == MCS_TILE_WARP) ++n_warp_tiles;
+    std::vector<uint8_t> tile_passes(n_tiles, 0);
+    int fast_passes = 0, n_fast = 0;
+    {
+        const char* env = getenv("MCS_TILED_FAST");   // experiments: 0 = per-pixel descriptors only
+        const bool want = !(env && atoi(env) == 0) && C == 3 && MCS_TILED_WARPS == 8;
+        if (want && e == cudaSuccess && n_warp_tiles > 0) {
+            uint8_t* d_counts = nullptr;
+            std::vector<uint8_t> counts(8 * (size_t)n_warp_tiles);
+            e = cudaMalloc(&d_counts, counts.size());
+            if (e == cudaSuccess) {
+                mcs_tile_fast_kernel<<<n_warp_tiles, 256>>>(d_tiles, d_layers, n_warp_tiles, nullptr, 0, 0, d_counts);
+                mcs_count_launch(1);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpy(counts.data(), d_counts, counts.size(), cudaMemcpyDeviceToHost);
+            if (d_counts) cudaFree(d_counts);
+            if (e == cudaSuccess) {
+                // A general pass costs about as much as one of the eight per-pixel slots it is meant to save
+                // (and more shared-memory wavefronts: its lanes hit random banks), so the group path only pays
+                // for tiles whose warps get by with ONE pass: at most 32 pixels per warp off the template.
+                const char* env_max = getenv("MCS_TILED_FAST_MAX");   // experiments
+                int limit = env_max ? atoi(env_max) : 32;
+                limit = std::max(0, std::min(limit, 32 * MCS_FAST_MAX_PASSES));
+                for (int i = 0; i < n_warp_tiles; ++i) {
+                    int mx = 0;
+                    for (int w = 0; w < 8; ++w) mx = std::max(mx, (int)counts[8 * (size_t)i + w]);
+                    if (mx > limit) continue;
+                    tiles[i].cls = MCS_TILE_FAST;
+                    tiles[i].flags = (short)((mx + 31) / 32);   // carried through the sort, then replaced by the cost
+                    ++n_fast;
+                }
+                if (n_fast > 0) {
+                    std::stable_sort(tiles.begin(), tiles.end(), by_class);
+                    for (int i = 0; i < n_fast; ++i) {
+                        tile_passes[i] = (uint8_t)tiles[i].flags;
+                        fast_passes = std::max(fast_passes, (int)tiles[i].flags);
+                    }
+                }
+            }
+        }
+    }
     h_cum[0] = 0;
     for (int i = 0; i < n_tiles; ++i) {
-        tiles[i].flags = (short)tile_cost(tiles[i]);
+        tiles[i].flags = (short)tile_cost(tiles[i], tile_passes[i]);
         h_cum[i + 1] = h_cum[i] + tiles[i].flags;
     }
+    for (int c = 0; c <= MCS_N_CLASSES; ++c) plan->class_first[c] = n_tiles;
     plan->class_first[0] = 0;
-    plan->class_first[1] = plan->class_first[2] = plan->class_first[3] = n_tiles;
-    for (int i = n_tiles - 1; i >= 0; --i) {
-        if (tiles[i].cls != MCS_TILE_WARP) plan->class_first[1] = i;
-        if (tiles[i].cls == MCS_TILE_ZERO) plan->class_first[2] = i;
+    for (int i = n_tiles - 1; i >= 0; --i) {   // segment s holds class MCS_N_CLASSES - 1 - s
+        for (int sgm = 1; sgm < MCS_N_CLASSES; ++sgm)
+            if (tiles[i].cls <= MCS_N_CLASSES - 1 - sgm) plan->class_first[sgm] = i;
     }
-    e = cudaMalloc(&d_sched, sizeof(int2) * MCS_SCHED_SLOTS * 3 * (MCS_SCHED_MAX_GRID + 1));
+    int4* d_issue = nullptr;
+    {
+        std::vector<int4> issue(n_tiles);
+        for (int i = 0; i < n_tiles; ++i) issue[i] = make_int4(tiles[i].layer, tiles[i].bx, tiles[i].by, tiles[i].reserved);
+        if (e == cudaSuccess) e = cudaMalloc(&d_issue, sizeof(int4) * n_tiles);
+        if (e == cudaSuccess) e = cudaMemcpy(d_issue, issue.data(), sizeof(int4) * n_tiles, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&d_sched, sizeof(int2) * MCS_SCHED_SLOTS * MCS_N_CLASSES * (MCS_SCHED_MAX_GRID + 1));
     if (e == cudaSuccess) e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_layers, plan->layers, sizeof(McsLayer) * MCS_MAX_LAYERS, cudaMemcpyHostToDevice);
-    // per-pixel descriptors of the WARP tiles (they come first in the sorted table)
+    // per-pixel descriptors of the FAST and WARP tiles (they come first in the sorted table); the FAST
+    // tiles keep theirs for launches whose output alignment rules the group path out
     uint32_t* d_desc = nullptr;
-    const int n_warp_tiles = plan->class_first[1];
+    uint8_t* d_fast = nullptr;
+    const int fast_stride = MCS_FAST_HEADER_BYTES + MCS_FAST_GROUP_BYTES + fast_passes * MCS_FAST_PASS_BYTES;
+    n_warp_tiles = plan->class_first[2];
     if (e == cudaSuccess && n_warp_tiles > 0) {
         e = cudaMalloc(&d_desc, sizeof(uint32_t) * MCS_CELL_W * MCS_CELL_H * (size_t)n_warp_tiles);
         if (e == cudaSuccess) {
             mcs_tile_desc_kernel<<<n_warp_tiles, 32 * MCS_TILED_WARPS>>>(d_tiles, d_layers, C, d_desc);
             mcs_count_launch(1);
             e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaDeviceSynchronize();
         }
+        if (e == cudaSuccess && n_fast > 0) {
+            e = cudaMalloc(&d_fast, (size_t)fast_stride * n_fast);
+            if (e == cudaSuccess) {
+                mcs_tile_fast_kernel<<<n_fast, 256>>>(d_tiles, d_layers, n_fast, d_fast, fast_stride, fast_passes, nullptr);
+                mcs_count_launch(1);
+                e = cudaGetLastError();
+            }
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
     }
     if (e != cudaSuccess) {
         why(plan, "tile upload failed: %s", cudaGetErrorString(e));
@@ -364,9 +540,15 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         cudaFree(d_layers);
         if (d_sched) cudaFree(d_sched);
         if (d_desc) cudaFree(d_desc);
+        if (d_fast) cudaFree(d_fast);
+        if (d_issue) cudaFree(d_issue);
         free(h_cum);
         return;
     }
+    plan->d_issue = d_issue;
+    plan->d_fast = d_fast;
+    plan->fast_stride = fast_stride;
+    plan->fast_passes = fast_passes;
     plan->d_desc = d_desc;
     {
         // frames per sweep of the tile table; $MCS_TILED_FRAME_BLOCK overrides (experiments)
