@@ -94,7 +94,6 @@ static_assert(sizeof(McsTile) == 32, "McsTile must stay 32 bytes");
 #define MCS_BOX_BYTES_MAX (40 * 1024)   // per staged source box
 
 #define MCS_FRAME_BLOCK_DEFAULT 64
-#define MCS_SCHED_SLOTS 4
 #define MCS_SCHED_MAX_GRID 2047
 
 struct mcs_plan {
@@ -142,16 +141,12 @@ struct mcs_plan {
     int cache_valid;
     int grid_ctas_per_sm;    // resident CTAs per SM of the tiled kernel (0 = not queried yet)
     int n_sm;
-    // Work split of the tiled kernel.  The (tile, frame) units, ordered tile-major, are cut into
-    // one contiguous range of equal estimated cost per CTA; h_cum[t] = summed per-frame cost of
-    // tiles 0..t-1.  The cut positions depend on (n_frames, grid) and are cached in a few slots.
-    long long* h_cum;        // host, n_tiles + 1 entries
+    // Work split of the tiled kernel: the CTAs claim chunks (a tile for one block of frames) at run time from
+    // d_work[0]; d_work[1] counts finished CTAs and the last one rewinds both, so a plan serves ONE launch at a
+    // time (one stream), see mcs.h.
     int class_first[MCS_N_CLASSES + 1];   // the tile table is sorted FAST, WARP, COPY, ZERO: first tile of each
                              // class, then n_tiles
-    int2* d_sched;           // device, MCS_SCHED_SLOTS x MCS_N_CLASSES x (MCS_SCHED_MAX_GRID + 1) entries {tile, frame}
-    int sched_frames[MCS_SCHED_SLOTS];
-    int sched_grid[MCS_SCHED_SLOTS];
-    int sched_next;          // slot overwritten next
+    unsigned* d_work;
 };
 
 

@@ -248,12 +248,11 @@ void mcs_plan_free_tiles(mcs_plan* plan) {
     if (plan->d_layers) cudaFree(plan->d_layers);
     if (plan->d_issue) cudaFree(plan->d_issue);
     plan->d_issue = nullptr;
-    if (plan->d_sched) cudaFree(plan->d_sched);
+    if (plan->d_work) cudaFree(plan->d_work);
     if (plan->d_desc) cudaFree(plan->d_desc);
     if (plan->d_fast) cudaFree(plan->d_fast);
     plan->d_desc = nullptr;
     plan->d_fast = nullptr;
-    free(plan->h_cum);
     for (int k = 0; k < MCS_MAX_LAYERS; ++k) {
         free(plan->h_row_span[k]);
         plan->h_row_span[k] = nullptr;
@@ -261,8 +260,7 @@ void mcs_plan_free_tiles(mcs_plan* plan) {
     plan->src_win_valid = 0;
     plan->d_tiles = nullptr;
     plan->d_layers = nullptr;
-    plan->d_sched = nullptr;
-    plan->h_cum = nullptr;
+    plan->d_work = nullptr;
     plan->tiled_ok = 0;
 }
 
@@ -434,14 +432,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         return a.cx0 < b.cx0;
     };
     std::stable_sort(tiles.begin(), tiles.end(), by_class);
-    long long* h_cum = static_cast<long long*>(malloc(sizeof(long long) * (n_tiles + 1)));
-    int2* d_sched = nullptr;
-    if (!h_cum) {
-        why(plan, "out of host memory");
-        cudaFree(d_tiles);
-        cudaFree(d_layers);
-        return;
-    }
+    unsigned* d_work = nullptr;
     e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_layers, plan->layers, sizeof(McsLayer) * MCS_MAX_LAYERS, cudaMemcpyHostToDevice);
 
@@ -491,11 +482,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             }
         }
     }
-    h_cum[0] = 0;
-    for (int i = 0; i < n_tiles; ++i) {
-        tiles[i].flags = (short)tile_cost(tiles[i], tile_passes[i]);
-        h_cum[i + 1] = h_cum[i] + tiles[i].flags;
-    }
+    for (int i = 0; i < n_tiles; ++i) tiles[i].flags = (short)tile_cost(tiles[i], tile_passes[i]);
     for (int c = 0; c <= MCS_N_CLASSES; ++c) plan->class_first[c] = n_tiles;
     plan->class_first[0] = 0;
     for (int i = n_tiles - 1; i >= 0; --i) {   // segment s holds class MCS_N_CLASSES - 1 - s
@@ -509,7 +496,8 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         if (e == cudaSuccess) e = cudaMalloc(&d_issue, sizeof(int4) * n_tiles);
         if (e == cudaSuccess) e = cudaMemcpy(d_issue, issue.data(), sizeof(int4) * n_tiles, cudaMemcpyHostToDevice);
     }
-    if (e == cudaSuccess) e = cudaMalloc(&d_sched, sizeof(int2) * MCS_SCHED_SLOTS * MCS_N_CLASSES * (MCS_SCHED_MAX_GRID + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_work, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(d_work, 0, 2 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemcpy(d_tiles, tiles.data(), sizeof(McsTile) * n_tiles, cudaMemcpyHostToDevice);
     // per-pixel descriptors of the FAST and WARP tiles (they come first in the sorted table); the FAST
     // tiles keep theirs for launches whose output alignment rules the group path out
@@ -538,11 +526,10 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         why(plan, "tile upload failed: %s", cudaGetErrorString(e));
         cudaFree(d_tiles);
         cudaFree(d_layers);
-        if (d_sched) cudaFree(d_sched);
+        if (d_work) cudaFree(d_work);
         if (d_desc) cudaFree(d_desc);
         if (d_fast) cudaFree(d_fast);
         if (d_issue) cudaFree(d_issue);
-        free(h_cum);
         return;
     }
     plan->d_issue = d_issue;
@@ -556,10 +543,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         const int v = env ? atoi(env) : 0;
         plan->frame_block = v > 0 ? v : MCS_FRAME_BLOCK_DEFAULT;
     }
-    plan->h_cum = h_cum;
-    plan->d_sched = d_sched;
-    for (int i = 0; i < MCS_SCHED_SLOTS; ++i) plan->sched_frames[i] = plan->sched_grid[i] = 0;
-    plan->sched_next = 0;
+    plan->d_work = d_work;
     plan->d_tiles = d_tiles;
     plan->d_layers = d_layers;
     plan->n_tiles = n_tiles;

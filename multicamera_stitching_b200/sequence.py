@@ -92,10 +92,14 @@ class SequencePipeline(object):
         d2h = int(self.slots[0]["dst"][0].numel())
         return h2d, d2h
 
-    def run(self, host_frames, host_out, lo=0, hi=None, ring=False):
+    def run(self, host_frames, host_out, lo=0, hi=None, ring=False, sync=True):
         """Composite frames ``[lo, hi)`` of the host sequence into
         ``host_out[lo:hi]``; returns the number of panoramas produced.  The
-        call returns after the last device->host copy has completed.
+        call returns after the last device->host copy has completed: the host
+        blocks on the download stream, so ``host_out`` may be read right away.
+        ``sync=False`` only orders the caller's current stream behind the
+        pipeline (a device-side dependency, the host does not wait): the caller
+        must synchronise that stream before it touches ``host_out``.
 
         ``ring=True``: the host tensors are rings of ``R`` frame-sets / panoramas and frame ``f``
         of the sequence lives in slot ``f % R`` (a long synthetic sequence cycled through a few
@@ -104,7 +108,7 @@ class SequencePipeline(object):
         F = int(host_out.shape[0])
         hi = F if hi is None else hi
         if ring:
-            return self._run_ring(host_frames, host_out, int(lo), int(hi), F)
+            return self._run_ring(host_frames, host_out, int(lo), int(hi), F, sync)
         with torch.cuda.device(self.device):
             start = torch.cuda.current_stream()
             for s in (self.s_in, self.s_k, self.s_out):
@@ -113,10 +117,16 @@ class SequencePipeline(object):
             for f0 in range(lo, hi, self.chunk):
                 self._chunk(i, host_frames, host_out, f0, min(self.chunk, hi - f0))
                 i += 1
-            start.wait_stream(self.s_out)
-            start.wait_stream(self.s_k)
-            start.wait_stream(self.s_in)
+            self._finish(start, sync)
         return hi - lo
+
+    def _finish(self, start, sync):
+        start.wait_stream(self.s_out)
+        start.wait_stream(self.s_k)
+        start.wait_stream(self.s_in)
+        if sync:
+            # the last chunk's download is the last operation of s_out, and every kernel and upload precedes one
+            self.s_out.synchronize()
 
     def _chunk(self, i, host_frames, host_out, f0, n):
         """Enqueue chunk ``i``: host frames ``[f0, f0 + n)`` -> slot -> kernel -> ``host_out[f0:f0 + n]``."""
@@ -152,14 +162,12 @@ class SequencePipeline(object):
             slot["ev_out"].record(self.s_out)
         slot["used"] = True
 
-    def _run_ring(self, host_frames, host_out, lo, hi, R):
+    def _run_ring(self, host_frames, host_out, lo, hi, R, sync=True):
         with torch.cuda.device(self.device):
             start = torch.cuda.current_stream()
             for s in (self.s_in, self.s_k, self.s_out):
                 s.wait_stream(start)
             for i, (r0, n) in enumerate(ring_chunks(lo, hi, R, self.chunk)):
                 self._chunk(i, host_frames, host_out, r0, n)
-            start.wait_stream(self.s_out)
-            start.wait_stream(self.s_k)
-            start.wait_stream(self.s_in)
+            self._finish(start, sync)
         return hi - lo

@@ -1,15 +1,20 @@
 """ORACLE (test infrastructure, never imported by the product package).
 
 CPU restatement of the reference's compositing and recalibration path, driving
-OpenCV exactly the way ``PostScripts/Stitcher/StitcherClass.py`` does.  The
-reference file itself cannot be imported under Python 3 (TabError at :527,
-``np.sort(dict.keys())`` at :61, missing ``extended_rospylogs``), so the
-algorithm is restated here function by function, each citing the lines it
-follows.  The arithmetic lives in OpenCV (third party, unpinned by the
-reference; opencv-python 4.13.0 here).  The reference ships no tests, fixtures
-or golden vectors: parity is pinned on cv2 itself, on the
-seeded synthetic inputs of ``multicamera_stitching_b200.synthetic`` and on the
-fixtures in ``tests/golden`` produced by this module.
+OpenCV exactly the way ``PostScripts/Stitcher/StitcherClass.py`` does, function
+by function, each citing the lines it follows.  The arithmetic lives in OpenCV
+(third party, unpinned by the reference; opencv-python 4.13.0 here).
+
+PINNED against the reference itself: the reference ships no tests or golden
+vectors, but its ``StitcherClass.py`` runs here once
+``oracle/build_ref.py`` has applied a four-line mechanical patch list (Python 2
+indentation and dict idioms, the OpenCV-version switch of the feature
+detector).  ``tests/test_oracle_ref_pin.py`` holds every function below against
+the reference method it restates - state fields, panoramas, match lists, bit
+for bit - on the seeded inputs of ``multicamera_stitching_b200.synthetic``, and
+``tests/golden/chain_ref.npz`` (``scripts/make_golden.py``) carries panoramas
+and stage states made by the reference's own classes to machines without the
+reference tree.
 
 State is carried in plain dicts with the reference's field names
 (StitcherClass.py:190-209).

@@ -9,6 +9,9 @@
                         get_projection_point_dst / _src, CalculateProjectionMatrix
   warp_cv2.npz          cv2.warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0) called as
                         StitcherClass.py:239 calls it, on a seeded noise image
+  chain_ref.npz         panoramas and stage states of the REFERENCE'S OWN Stitcher / StitcherBase classes
+                        (StitcherClass.py made importable by oracle/build_ref.py): 3-, 4- (super mode) and 6-camera
+                        chains calibrated by calibrate_stitcher on injected stage homographies
   chain_cv2.npz         the 3-camera warp+paste chain of StitcherClass.py:131-136 / :239-241
                         (oracle/stitcher_ref.py driving cv2), with its geometry (:293-351)
   match_cv2.npz         cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) + the ratio loop of :428-433
@@ -100,6 +103,51 @@ def golden_chain():
         geo["ABSize_%d" % k] = np.asarray(s["ABSize"], dtype=np.int64)
         geo["limits_%d" % k] = np.asarray([s["x_limits"], s["y_limits"]], dtype=np.int64)
     np.savez_compressed(os.path.join(OUT, "chain_cv2.npz"), pano=pano, **geo)
+
+
+CHAIN_REF_CASES = {
+    # name: (cameras, height, width, super_mode, frame kind, xoffset, yoffset)  -- offsets of calibrate_stitcher are 0
+    "c3": (3, 96, 128, False, "noise"),
+    "c4_super": (4, 90, 160, True, "noise"),
+    "c6": (6, 68, 120, False, "smooth"),
+}
+
+
+def chain_ref_homographies(st, n, h, w):
+    """The stage homographies ``helpers.synthetic_chain`` uses (they depend on the running canvas width)."""
+    from multicamera_stitching_b200 import synthetic
+    homs, cw = [], w
+    for k in range(n - 1):
+        homs.append(synthetic.make_homography(k, h, w, cw))
+        cw = st.stitchers[k].result_shape()[1]
+    return homs
+
+
+def golden_chain_ref():
+    """Panoramas and stage states produced by the REFERENCE'S OWN Stitcher / StitcherBase classes
+    (oracle/build_ref.py makes StitcherClass.py importable): calibrate_stitcher (:77-112) runs its real
+    canvas geometry (:293-351) on injected stage homographies, stitch (:114-136, :211-256) makes the panorama."""
+    from helpers import synthetic_chain
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is None:
+        raise SystemExit("make_golden.py: the reference tree is needed for chain_ref.npz")
+    out = {}
+    for name, (n, h, w, super_mode, kind) in CHAIN_REF_CASES.items():
+        st, states, labels, images = synthetic_chain(n, h, w, 3, super_mode=super_mode, kind=kind)
+        rs = ref.Stitcher(images, super_mode=super_mode)
+        for sb, H in zip(rs.stitchers, chain_ref_homographies(st, n, h, w)):
+            sb.detectAndDescribe = lambda image: (np.zeros((1, 2), np.float32), None)
+            sb.matchKeypoints = (lambda Hk: (lambda **kw: (np.array(Hk, dtype=np.float64), [(0, 0)] * 5,
+                                                          np.ones((5, 1), np.uint8))))(H)
+        rs.calibrate_stitcher(images, save=False)
+        out[name + "_pano"] = rs.stitch(images)
+        for k, sb in enumerate(rs.stitchers):
+            out["%s_cachedAH_%d" % (name, k)] = np.asarray(sb.cachedAH, dtype=np.float64)
+            out["%s_Bpts_%d" % (name, k)] = np.asarray(sb.Bpts, dtype=np.int64)
+            out["%s_ABSize_%d" % (name, k)] = np.asarray(sb.ABSize, dtype=np.int64)
+            out["%s_limits_%d" % (name, k)] = np.asarray([sb.x_limits, sb.y_limits], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "chain_ref.npz"), **out)
 
 
 def match_descriptors():
@@ -201,6 +249,7 @@ if __name__ == "__main__":
     golden_utils(ref_root)
     golden_warp()
     golden_chain()
+    golden_chain_ref()
     golden_match()
     golden_resize()
     golden_prewarp(ref_root)
@@ -208,6 +257,8 @@ if __name__ == "__main__":
     with open(os.path.join(OUT, "README.md"), "w") as f:
         f.write("Fixtures written by scripts/make_golden.py (cv2 %s, numpy %s).\n"
                 "utils_reference.npz comes from the reference's own Calibration_Utils/Utils.py;\n"
+                "chain_ref.npz from the reference's own StitcherClass.py (Stitcher.calibrate_stitcher + stitch, made\n"
+                "importable by oracle/build_ref.py) on injected stage homographies;\n"
                 "recorded_reference.json is what the reference's MediaPlayer/model.py data_reader parses from\n"
                 "recorded_data.csv; the others come from cv2 driven as PostScripts/Stitcher/StitcherClass.py\n"
                 "drives it.\n"

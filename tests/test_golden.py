@@ -65,6 +65,25 @@ def test_chain_oracle_reproduces_golden_panorama_and_geometry():
             assert np.array_equal(np.asarray([obj["x_limits"], obj["y_limits"]]), g["limits_%d" % k])
 
 
+@pytest.mark.parametrize("case", ["c3", "c4_super", "c6"])
+def test_chain_oracle_reproduces_the_reference_classes_golden(case):
+    """chain_ref.npz was produced by the reference's own Stitcher / StitcherBase (scripts/make_golden.py through
+    oracle/build_ref.py): the oracle restatement and the product's host-side state reproduce it."""
+    from helpers import synthetic_chain
+    mg = _gen()
+    g = load("chain_ref.npz")
+    n, h, w, super_mode, kind = mg.CHAIN_REF_CASES[case]
+    st, states, labels, images = synthetic_chain(n, h, w, 3, super_mode=super_mode, kind=kind)
+    pano = stitcher_ref.stitch_chain(states, labels, images)
+    assert pano.shape == g[case + "_pano"].shape and np.array_equal(pano, g[case + "_pano"])
+    for k, (s, sb) in enumerate(zip(states, st.stitchers)):
+        for obj in (s, {f: getattr(sb, f) for f in ("cachedAH", "Bpts", "ABSize", "x_limits", "y_limits")}):
+            assert np.array_equal(np.asarray(obj["cachedAH"]), g["%s_cachedAH_%d" % (case, k)])
+            assert np.array_equal(np.asarray(obj["Bpts"]), g["%s_Bpts_%d" % (case, k)])
+            assert np.array_equal(np.asarray(obj["ABSize"]), g["%s_ABSize_%d" % (case, k)])
+            assert np.array_equal(np.asarray([obj["x_limits"], obj["y_limits"]]), g["%s_limits_%d" % (case, k)])
+
+
 def test_match_model_reproduces_bfmatcher_golden():
     g = load("match_cv2.npz")
     idx, dist, keep, matches = match_model.match(g["fa"], g["fb"], 0.75)
@@ -137,6 +156,19 @@ def test_gpu_chain_equals_golden_panorama(cuda_device):
     st, states, labels, images = synthetic_chain(3, 96, 128, 3, kind="noise", xoffset=3, yoffset=5)
     got = st.stitch(images)
     assert got.shape == g["pano"].shape and np.array_equal(got, g["pano"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["c3", "c4_super", "c6"])
+def test_gpu_chain_equals_the_reference_classes_golden(cuda_device, case):
+    """The CUDA path against panoramas made by the reference's own classes (chain_ref.npz)."""
+    from helpers import synthetic_chain
+    mg = _gen()
+    g = load("chain_ref.npz")
+    n, h, w, super_mode, kind = mg.CHAIN_REF_CASES[case]
+    st, states, labels, images = synthetic_chain(n, h, w, 3, super_mode=super_mode, kind=kind)
+    got = st.stitch(images)
+    assert got.shape == g[case + "_pano"].shape and np.array_equal(got, g[case + "_pano"])
 
 
 @pytest.mark.gpu

@@ -47,6 +47,31 @@ def test_pipeline_with_window_uploads_equals_the_cv2_chain(cuda_device, n, h, w,
     assert torch.equal(out, out2)
 
 
+def test_run_returns_with_the_panoramas_on_the_host(cuda_device):
+    """``run()`` blocks until the last download has landed: the host buffer is read straight after the
+    call, with no synchronize in between, on a batch long enough for the copies to still be in flight if
+    the call only ordered streams; ``sync=False`` is the asynchronous form."""
+    st, states, labels, images = synthetic_chain(6, 540, 960, 3, kind="noise")
+    shapes = [images[l].shape for l in labels]
+    F = 24
+    host = {l: pinned_like((F,) + tuple(images[l].shape)) for l in labels}
+    for l in labels:
+        for f in range(F):
+            host[l][f].copy_(torch.from_numpy(images[l]))
+    pipe = SequencePipeline(st, shapes, cuda_device, chunk=4, depth=3)
+    ref = stitcher_ref.stitch_chain(states, labels, images)
+    out = pinned_like((F,) + pipe.plan.out_shape())
+    for _ in range(3):
+        out.fill_(0x5A)
+        assert pipe.run(host, out) == F
+        last = out[F - 1].numpy().copy()          # no torch.cuda.synchronize() before this read
+        assert np.array_equal(last, ref)
+    out.fill_(0x5A)
+    pipe.run(host, out, sync=False)
+    torch.cuda.current_stream().synchronize()     # the caller's stream was ordered behind the pipeline
+    assert np.array_equal(out[F - 1].numpy(), ref) and np.array_equal(out[0].numpy(), ref)
+
+
 def test_feather_mode_uploads_whole_frames(cuda_device):
     st, states, labels, images = synthetic_chain(3, 120, 200, 3, kind="noise")
     st.feather_log2 = 2
