@@ -266,6 +266,23 @@ int mcs_match_hamming_top2(const uint8_t* q, const int32_t* nq, int nq_max,
                            int batch, void* cuda_stream);
 
 /*
+ * mcs_match_l2_top2 - the same for float32 descriptors and the L2 norm: the reference's own matcher
+ * branch (SIFT descriptors, 128 floats, cv2.DescriptorMatcher_create("BruteForce") = NORM_L2,
+ * StitcherClass.py:380-386 and :423-433).
+ *
+ *   q, t        device, [batch][nq_max|nt_max][dim] float32 descriptors, dim <= 256
+ *   dist2       device float32 [batch][nq_max][2]: sqrtf of the float32 sum of squared differences,
+ *               as cv2.BFMatcher(NORM_L2) reports it (bit-identical for integer-valued descriptors
+ *               such as OpenCV's SIFT, whose sums are exact in float32); -1 where absent
+ * Everything else as mcs_match_hamming_top2.
+ */
+int mcs_match_l2_top2(const float* q, const int32_t* nq, int nq_max,
+                      const float* t, const int32_t* nt, int nt_max,
+                      int dim, double ratio,
+                      int32_t* idx2, float* dist2, uint8_t* keep,
+                      int batch, void* cuda_stream);
+
+/*
  * mcs_ransac_homography - score `k` 4-point homography hypotheses per pair,
  * one warp per hypothesis.
  *

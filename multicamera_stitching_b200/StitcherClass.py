@@ -135,9 +135,31 @@ class Stitcher(Debugger):
         out = _composite(self._engine_(), self.stitchers, frames, batched=False, debugger=self,
                          feather_log2=getattr(self, "feather_log2", 0))
         if draw_descriptors and not _is_tensor(out):
-            # the reference draws every stage's overlay into the canvas it produced (:244-245);
-            # only the last stage's overlay is in final-panorama coordinates
-            out = self.stitchers[-1].draw_descriptors(img_src=out)
+            out = self._draw_overlays(out, frames)
+        return out
+
+    def _draw_overlays(self, out, frames):
+        """The reference draws every stage's overlay into the canvas that stage produced, before the optional
+        crop (:244-251); the canvas is then pasted verbatim by the next stage, so in the final panorama the
+        overlays lie on top of everything, earlier stages below later ones, each at its canvas' position and
+        clipped to what is left of that canvas."""
+        try:
+            flat = self.plan([f.shape for f in frames]).flat
+        except Exception:   # segmented chains (a resized canvas in between): only the last stage is in final coordinates
+            flat = None
+        if flat is None or (flat.out_h, flat.out_w) != tuple(out.shape[:2]):
+            return self.stitchers[-1].draw_descriptors(img_src=out)
+        by_cam = {l.cam: l for l in flat.layers}
+        for s, st in enumerate(self.stitchers):
+            if st.cachedAH is None or (s + 1) not in by_cam:
+                continue
+            l = by_cam[s + 1]
+            x0, y0, x1, y1 = (int(v) for v in l.rect)
+            if x1 <= x0 or y1 <= y0:
+                continue
+            sub = np.ascontiguousarray(out[y0:y1, x0:x1])
+            st.draw_descriptors(sub, offset=(l.ox - x0, l.oy - y0), canvas_size=st.ABSize)
+            out[y0:y1, x0:x1] = sub
         return out
 
     def stitch_batch(self, frames_dic, out=None):
@@ -180,6 +202,10 @@ class Stitcher(Debugger):
                     loaded = _load_pickle(f)
                 for st in loaded.stitchers:
                     st.params_to_array()
+                # a Python-2 pickle read with encoding="latin1" may carry the labels as a bytes ('S') array:
+                # images_dic is keyed by str
+                loaded.img_labels = np.array([l.decode("latin1") if isinstance(l, bytes) else str(l)
+                                              for l in loaded.img_labels])
                 loaded.debugger(DEBUG_LEVEL_0, "[STITCHER]: Stitcher configuration loaded from file")
             else:
                 self.debugger(DEBUG_LEVEL_0, "[STITCHER]: No Stitcher configuration file", log_type="warn")
@@ -194,11 +220,14 @@ class Stitcher(Debugger):
 class StitcherBase(Debugger):
     """One pair (imageB = running canvas, imageA = next camera), reference :180-529."""
 
+    # Class-level defaults: objects unpickled from a configuration the REFERENCE saved are built without
+    # __init__ and carry only the reference's fields (:190-209); re-calibrating one must still work.
+    descriptor = "ORB"    # BASELINE.json config 4; "SIFT" = the reference's detector (float descriptors, L2 matching)
+    nfeatures = 2000
+
     def __init__(self, sid=None, super_mode=False):
         self.sid = sid
         self.super_mode = super_mode
-        self.descriptor = "ORB"   # BASELINE.json config 4; "SIFT" = the reference's detector
-        self.nfeatures = 2000
         self.reset()
 
     def reset(self):
@@ -349,29 +378,42 @@ class StitcherBase(Debugger):
         from . import recalib
         return recalib.match_keypoints(kpsA, kpsB, featuresA, featuresB, ratio, reprojThresh)
 
-    def draw_descriptors(self, img_src):
-        """Debug overlay of corners / ROI limits (reference :450-483)."""
+    def draw_descriptors(self, img_src, offset=(0, 0), canvas_size=None):
+        """Debug overlay of corners / ROI limits, drawn exactly like the reference's (:450-483, text through
+        Calibration_Utils.print_list_text).  ``offset`` / ``canvas_size`` (extension): draw the overlay of a stage
+        whose canvas origin sits at ``offset`` inside ``img_src`` and whose canvas is ``canvas_size = (w, h)`` -
+        how ``Stitcher.stitch`` puts every stage's overlay into the final panorama."""
+        dx, dy = int(offset[0]), int(offset[1])
+        cw, ch = (img_src.shape[1], img_src.shape[0]) if canvas_size is None else (int(canvas_size[0]), int(canvas_size[1]))
         white = (255, 255, 255)
+
+        def shifted(pts):
+            return [(int(p[0]) + dx, int(p[1]) + dy) for p in pts]
+
         if self.Bpts is not None:
-            cv2.drawContours(img_src, np.array([self.Bpts], dtype=np.int32), -1, white, 1)
-            for pt in self.Bpts:
-                p = (int(pt[0]), int(pt[1]))
+            pts = shifted(self.Bpts)
+            cv2.drawContours(image=img_src, contours=np.array([pts]), contourIdx=-1, color=white, thickness=1)
+            for p in pts:
                 cv2.circle(img_src, p, 2, (0, 0, 255), -1)
                 cv2.circle(img_src, p, 5, (0, 255, 255), 1)
         if self.Apts is not None:
-            cv2.drawContours(img_src, np.array([self.Apts], dtype=np.int32), -1, white, 1)
-            for pt in self.Apts:
-                p = (int(pt[0]), int(pt[1]))
+            pts = shifted(self.Apts)
+            cv2.drawContours(image=img_src, contours=np.array([pts]), contourIdx=-1, color=white, thickness=1)
+            for p in pts:
                 cv2.circle(img_src, p, 2, (0, 0, 255), -1)
                 cv2.circle(img_src, p, 3, (255, 255, 0), 1)
         if self.x_limits is not None:
             for v in self.x_limits:
-                cv2.line(img_src, (int(v), 0), (int(v), img_src.shape[0]), (0, 255, 0), 1)
+                cv2.line(img=img_src, pt1=(int(v) + dx, dy), pt2=(int(v) + dx, ch + dy), color=(0, 255, 0), thickness=1)
         if self.y_limits is not None:
             for v in self.y_limits:
-                cv2.line(img_src, (0, int(v)), (img_src.shape[1], int(v)), (255, 255, 0), 1)
-        cv2.putText(img_src, "{}".format(self.sid), (20, 20), cv2.FONT_HERSHEY_SIMPLEX, 0.60,
-                    (0, 255, 255), 1, cv2.LINE_AA)
+                cv2.line(img=img_src, pt1=(dx, int(v) + dy), pt2=(cw + dx, int(v) + dy), color=(255, 255, 0), thickness=1)
+        # print_list_text(str_list=[sid], origin=(20, 20), color=(0, 255, 255), thickness=1, fontScale=0.60):
+        # a black outline under the coloured text (Utils.py:271-307)
+        for colour, thick in (((0, 0, 0), 4), ((0, 255, 255), 1)):
+            cv2.putText(img=img_src, text="{}".format(self.sid), org=(20 + dx, 20 + dy),
+                        fontFace=cv2.FONT_HERSHEY_SIMPLEX, fontScale=0.60, color=colour, thickness=thick,
+                        lineType=cv2.LINE_AA, bottomLeftOrigin=False)
         return img_src
 
     # -- persistence helpers -----------------------------------------------------

@@ -25,7 +25,7 @@ EXPORTS = (
     "mcs_plan_owned_pixels", "mcs_plan_source_windows", "mcs_plan_source_spans", "mcs_copy_window_u8", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_last_variant",
     "mcs_plan_force_variant", "mcs_plan_rows_need_padding", "mcs_plan_promise_padded_rows",
     "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_plan_tiled_stats", "mcs_launch_count",
-    "mcs_match_hamming_top2", "mcs_ransac_homography", "mcs_resize_linear_u8",
+    "mcs_match_hamming_top2", "mcs_match_l2_top2", "mcs_ransac_homography", "mcs_resize_linear_u8",
 )
 
 
@@ -105,6 +105,9 @@ def load(build_if_missing=False):
     lib.mcs_match_hamming_top2.argtypes = [_vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_double, _vp, _vp, _vp, ctypes.c_int, _vp]
     lib.mcs_ransac_homography.restype = ctypes.c_int
+    lib.mcs_match_l2_top2.restype = ctypes.c_int
+    lib.mcs_match_l2_top2.argtypes = [_vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                      _vp, _vp, _vp, ctypes.c_int, _vp]
     lib.mcs_ransac_homography.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_float,
                                           _vp, _vp, _vp, _vp, ctypes.c_int, _vp]
     lib.mcs_resize_linear_u8.restype = ctypes.c_int

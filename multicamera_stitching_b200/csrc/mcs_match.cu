@@ -149,3 +149,149 @@ extern "C" int mcs_match_hamming_top2(const uint8_t* q, const int32_t* nq, int n
     }
     return MCS_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// Brute-force L2 2-NN + ratio test for float32 descriptors: the reference's own matcher branch
+// (SIFT, 128 floats, cv2.DescriptorMatcher_create("BruteForce") = NORM_L2, StitcherClass.py:380-386,
+// :423-433).
+//
+// distance = sqrtf(sum_k (a_k - b_k)^2), the difference form OpenCV's normL2Sqr uses (no
+// |a|^2 + |b|^2 - 2ab expansion: that form cancels).  SIFT descriptors as OpenCV emits them are
+// integer-valued floats in 0..255, so every square and every partial sum (< 128 * 255^2 < 2^24) is exact
+// in float32 whatever the order of summation: distances, neighbour order and ratio decisions are then
+// bit-identical to cv2's.  For other float descriptors the sum is rounded in this kernel's order
+// (k ascending, one accumulator), which may differ from OpenCV's SIMD order in the last bit.
+//
+// No tensor cores: the work is 2000 x 2000 x 128 x 4 pairs = 2 GFLOP of FP32 multiply-adds, tens of
+// microseconds on the FMA pipe next to a second of CPU SIFT detection per frame, and an MMA would need
+// the cancelling expansion above.
+//
+// Layout: a CTA owns 32 queries and sweeps the train set in chunks of 128; both tiles sit in shared memory
+// with a row pitch of DIM + 1 floats (conflict-free column walks).  Thread (ty, lane) accumulates the 4 x 4
+// distances between queries 4 ty .. 4 ty + 3 and trains lane, lane + 32, lane + 64, lane + 96 of the chunk,
+// keeps a running top-2 per query (packed key: distance bits << 32 | train index, which orders
+// non-negative floats numerically and breaks ties toward the lower index), and the 32 lanes merge by
+// shuffles at the end.
+#define L2_QB 32
+#define L2_TB 128
+#define L2_THREADS 256
+
+__device__ __forceinline__ void top2_insert64(unsigned long long key, unsigned long long& k0, unsigned long long& k1) {
+    const unsigned long long hi = k0 > key ? k0 : key;
+    k0 = k0 < key ? k0 : key;
+    k1 = k1 < hi ? k1 : hi;
+}
+
+__global__ void __launch_bounds__(L2_THREADS)
+mcs_match_l2_kernel(const float* __restrict__ q, const int32_t* __restrict__ nq_arr, int nq_max,
+                    const float* __restrict__ t, const int32_t* __restrict__ nt_arr, int nt_max, int dim,
+                    double ratio, int32_t* __restrict__ idx2, float* __restrict__ dist2, uint8_t* __restrict__ keep) {
+    extern __shared__ float s_l2[];
+    const int pitch = dim + 1;
+    float* s_q = s_l2;                    // [L2_QB][pitch]
+    float* s_t = s_l2 + L2_QB * pitch;    // [L2_TB][pitch]
+    const int pair = blockIdx.y;
+    const int nq = nq_arr ? min(nq_arr[pair], nq_max) : nq_max;
+    const int nt = nt_arr ? min(nt_arr[pair], nt_max) : nt_max;
+    const int q0 = blockIdx.x * L2_QB;
+    if (q0 >= nq_max) return;
+    const int ty = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* qp = q + (size_t)pair * nq_max * dim;
+    const float* tp = t + (size_t)pair * nt_max * dim;
+
+    for (int i = threadIdx.x; i < L2_QB * dim; i += L2_THREADS) {
+        const int r = i / dim, k = i - r * dim;
+        s_q[r * pitch + k] = q0 + r < nq ? __ldg(qp + (size_t)(q0 + r) * dim + k) : 0.0f;
+    }
+    const unsigned long long none = ~0ull;
+    unsigned long long b0[4], b1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b0[i] = b1[i] = none;
+
+    for (int c0 = 0; c0 < nt; c0 += L2_TB) {
+        const int cn = min(L2_TB, nt - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < L2_TB * dim; i += L2_THREADS) {
+            const int r = i / dim, k = i - r * dim;
+            s_t[r * pitch + k] = r < cn ? __ldg(tp + (size_t)(c0 + r) * dim + k) : 0.0f;
+        }
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+        for (int k = 0; k < dim; ++k) {
+            float qa[4], tb[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) qa[a] = s_q[(4 * ty + a) * pitch + k];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) tb[b] = s_t[(lane + 32 * b) * pitch + k];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const float d = __fsub_rn(qa[a], tb[b]);
+                    acc[a][b] = __fadd_rn(acc[a][b], __fmul_rn(d, d));   // like the reference build: no contraction
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = lane + 32 * b;
+                if (j < cn)
+                    top2_insert64(((unsigned long long)__float_as_uint(acc[a][b]) << 32) | (unsigned)(c0 + j), b0[a], b1[a]);
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        unsigned long long k0 = b0[a], k1 = b1[a];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, off);
+            const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off);
+            const unsigned long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0;
+            const unsigned long long m1 = k1 < o1 ? k1 : o1;
+            k1 = hi < m1 ? hi : m1;
+            k0 = lo;
+        }
+        const int qidx = q0 + 4 * ty + a;
+        if (lane == 0 && qidx < nq_max) {
+            const size_t o = (size_t)pair * nq_max + qidx;
+            const bool valid_q = qidx < nq;
+            const bool h0 = valid_q && k0 != none, h1 = valid_q && k1 != none;
+            const float d0 = sqrtf(__uint_as_float((unsigned)(k0 >> 32))), d1 = sqrtf(__uint_as_float((unsigned)(k1 >> 32)));
+            idx2[2 * o] = h0 ? (int)(unsigned)k0 : -1;
+            idx2[2 * o + 1] = h1 ? (int)(unsigned)k1 : -1;
+            dist2[2 * o] = h0 ? d0 : -1.0f;
+            dist2[2 * o + 1] = h1 ? d1 : -1.0f;
+            // `m[0].distance < m[1].distance * ratio`: float32 distances promoted to Python floats
+            keep[o] = (h0 && h1 && (double)d0 < __dmul_rn((double)d1, ratio)) ? 1 : 0;
+        }
+    }
+}
+
+extern "C" int mcs_match_l2_top2(const float* q, const int32_t* nq, int nq_max, const float* t, const int32_t* nt,
+                                 int nt_max, int dim, double ratio, int32_t* idx2, float* dist2, uint8_t* keep,
+                                 int batch, void* cuda_stream) {
+    MCS_CHECK_ARG(batch >= 0 && batch <= 65535, "mcs_match_l2_top2: batch=%d outside 0..65535", batch);
+    MCS_CHECK_ARG(nq_max >= 0 && nt_max >= 0, "mcs_match_l2_top2: nq_max=%d nt_max=%d out of range", nq_max, nt_max);
+    MCS_CHECK_ARG(dim >= 1 && dim <= 256, "mcs_match_l2_top2: dim=%d outside 1..256", dim);
+    if (batch == 0 || nq_max == 0) return MCS_OK;
+    MCS_CHECK_ARG(q && idx2 && dist2 && keep && (t || nt_max == 0), "mcs_match_l2_top2: NULL buffer");
+    const size_t smem = (size_t)(L2_QB + L2_TB) * (dim + 1) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(mcs_match_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        dim3 grid((nq_max + L2_QB - 1) / L2_QB, batch, 1);
+        mcs_match_l2_kernel<<<grid, L2_THREADS, smem, (cudaStream_t)cuda_stream>>>(q, nq, nq_max, t, nt, nt_max, dim, ratio,
+                                                                                   idx2, dist2, keep);
+        mcs_count_launch(1);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        mcs_set_error("mcs_match_l2_top2: launch failed: %s", cudaGetErrorString(e));
+        return MCS_ERR_CUDA;
+    }
+    return MCS_OK;
+}

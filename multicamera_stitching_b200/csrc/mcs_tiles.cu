@@ -459,10 +459,13 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             if (d_counts) cudaFree(d_counts);
             if (e == cudaSuccess) {
                 // A general pass costs about as much as one of the eight per-pixel slots it is meant to save
-                // (and more shared-memory wavefronts: its lanes hit random banks), so the group path only pays
-                // for tiles whose warps get by with ONE pass: at most 32 pixels per warp off the template.
+                // (and more shared-memory wavefronts: its lanes hit random banks).  Measured on config 2, whose
+                // cameras step 0.93 - 1.13 source pixels per output pixel: with up to 64 pixels per warp off the
+                // template (two passes, 86 % of the tiles) 0.877 ms per 64 panoramas against 0.833 ms for the
+                // per-pixel path, with up to 32 (one pass, 20 % of the tiles) 0.837 against 0.821.  The group path
+                // is therefore kept for tiles that are really at unit scale: at most 12 pixels per warp (5 %) off.
                 const char* env_max = getenv("MCS_TILED_FAST_MAX");   // experiments
-                int limit = env_max ? atoi(env_max) : 32;
+                int limit = env_max ? atoi(env_max) : 12;
                 limit = std::max(0, std::min(limit, 32 * MCS_FAST_MAX_PASSES));
                 for (int i = 0; i < n_warp_tiles; ++i) {
                     int mx = 0;

@@ -28,28 +28,30 @@ def _ptr(t):
 
 # ---------------------------------------------------------------------------
 def match_top2_batch(q, t, nq=None, nt=None, ratio=0.75):
-    """Brute-force Hamming 2-NN + ratio test for a batch of pairs.
+    """Brute-force 2-NN + ratio test for a batch of pairs: Hamming distance for uint8 (binary, e.g. ORB)
+    descriptors, L2 for float32 ones (the reference's SIFT branch, StitcherClass.py:380-386, :423-424).
 
-    ``q``: uint8 CUDA tensor [B, NQ, D] (query = featuresA), ``t``: [B, NT, D]
+    ``q``: CUDA tensor [B, NQ, D] (query = featuresA), ``t``: [B, NT, D]
     (train = featuresB); ``nq``/``nt``: optional int32 CUDA tensors [B] with the
-    real counts.  Returns ``(idx2 [B,NQ,2] int32, dist2 [B,NQ,2] int32, keep
+    real counts.  Returns ``(idx2 [B,NQ,2] int32, dist2 [B,NQ,2] int32 | float32, keep
     [B,NQ] uint8)`` on the device."""
     lib = _cabi.load()
-    if q.dtype != torch.uint8 or t.dtype != torch.uint8 or not q.is_cuda or not t.is_cuda:
-        raise TypeError("descriptors must be uint8 CUDA tensors")
+    if not q.is_cuda or not t.is_cuda or q.dtype != t.dtype or q.dtype not in (torch.uint8, torch.float32):
+        raise TypeError("descriptors must be uint8 or float32 CUDA tensors of one dtype")
     q = q.contiguous()
     t = t.contiguous()
     B, NQ, D = q.shape
     NT = t.shape[1]
+    binary = q.dtype == torch.uint8
     idx2 = torch.empty((B, NQ, 2), dtype=torch.int32, device=q.device)
-    dist2 = torch.empty((B, NQ, 2), dtype=torch.int32, device=q.device)
+    dist2 = torch.empty((B, NQ, 2), dtype=torch.int32 if binary else torch.float32, device=q.device)
     keep = torch.empty((B, NQ), dtype=torch.uint8, device=q.device)
     with torch.cuda.device(q.device):
         stream = torch.cuda.current_stream().cuda_stream
-        _cabi.check(lib.mcs_match_hamming_top2(_ptr(q), _ptr(nq), NQ, _ptr(t), _ptr(nt), NT, D,
-                                               float(ratio), _ptr(idx2), _ptr(dist2), _ptr(keep),
-                                               B, ctypes.c_void_p(stream)),
-                    "mcs_match_hamming_top2")
+        fn = lib.mcs_match_hamming_top2 if binary else lib.mcs_match_l2_top2
+        _cabi.check(fn(_ptr(q), _ptr(nq), NQ, _ptr(t), _ptr(nt), NT, D, float(ratio), _ptr(idx2), _ptr(dist2),
+                       _ptr(keep), B, ctypes.c_void_p(stream)),
+                    "mcs_match_hamming_top2" if binary else "mcs_match_l2_top2")
     return idx2, dist2, keep
 
 
@@ -182,55 +184,105 @@ def refine_homography(H, a, b, iters=REFINE_ITERS):
     return np.append(h, 1.0).reshape(3, 3)
 
 
-def find_homography_ransac(ptsA, ptsB, reproj_thresh, max_iters=RANSAC_MAX_ITERS, seed=RANSAC_SEED):
-    """GPU RANSAC (hypothesis scoring) + host refit on the winner's inliers.
-    Returns ``(H 3x3 float64 | None, status N x 1 uint8 | None)`` like
-    ``cv2.findHomography(ptsA, ptsB, cv2.RANSAC, reproj_thresh)``."""
-    dev = _device()
-    ptsA = np.ascontiguousarray(ptsA, dtype=np.float32).reshape(-1, 2)
-    ptsB = np.ascontiguousarray(ptsB, dtype=np.float32).reshape(-1, 2)
-    n = len(ptsA)
-    if n < 4:
-        return None, None
-    samples = draw_samples(n, max_iters, seed)
-    a = torch.from_numpy(ptsA).to(dev)[None]
-    b = torch.from_numpy(ptsB).to(dev)[None]
-    s = torch.from_numpy(samples).to(dev)[None]
-    counts, H_k, best, mask = ransac_batch(a, b, s, reproj_thresh)
-    best_i = int(best[0].item())
-    if best_i < 0:
-        return None, None
-    status = mask[0].cpu().numpy().reshape(-1, 1)
+def _refit(ptsA, ptsB, H0, status):
+    """Host end of ``cv2.findHomography``: least-squares fit on the winner's inliers + LM refinement."""
     inl = status.ravel().astype(bool)
-    H = H_k[0, best_i].cpu().numpy().reshape(3, 3)
+    H = H0
     if inl.sum() >= 4:
         if inl.sum() > 4:
             H = fit_homography_dlt(ptsA[inl], ptsB[inl])
         H = refine_homography(H, ptsA[inl], ptsB[inl])
-    return H, status
+    return H
+
+
+def find_homography_ransac_batch(pairs, reproj_thresh, max_iters=RANSAC_MAX_ITERS, seed=RANSAC_SEED):
+    """``cv2.findHomography(ptsA, ptsB, cv2.RANSAC, reproj_thresh)`` for several point-set pairs at once: ONE
+    hypothesis-scoring launch over all pairs (padded to the longest), one device->host copy, then the refit of
+    every pair on the host.  ``pairs``: list of ``(ptsA, ptsB)`` float32 N_i x 2.  Returns a list of
+    ``(H 3x3 float64 | None, status N_i x 1 uint8 | None)``."""
+    dev = _device()
+    pts = [(np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 2), np.ascontiguousarray(b, dtype=np.float32).reshape(-1, 2))
+           for a, b in pairs]
+    out = [(None, None)] * len(pts)
+    todo = [i for i, (a, _) in enumerate(pts) if len(a) >= 4]
+    if not todo:
+        return out
+    n_max = max(len(pts[i][0]) for i in todo)
+    B = len(todo)
+    hA = np.zeros((B, n_max, 2), np.float32)
+    hB = np.zeros((B, n_max, 2), np.float32)
+    hS = np.zeros((B, max_iters, 4), np.int32)
+    hN = np.zeros((B,), np.int32)
+    for j, i in enumerate(todo):
+        a, b = pts[i]
+        hA[j, :len(a)] = a
+        hB[j, :len(b)] = b
+        hN[j] = len(a)
+        hS[j] = draw_samples(len(a), max_iters, seed)
+    a_d, b_d = torch.from_numpy(hA).to(dev), torch.from_numpy(hB).to(dev)
+    counts, H_k, best, mask = ransac_batch(a_d, b_d, torch.from_numpy(hS).to(dev), reproj_thresh,
+                                           n=torch.from_numpy(hN).to(dev))
+    best_h = best.cpu().numpy()                      # one synchronisation for the whole batch
+    mask_h = mask.cpu().numpy()
+    H_best = H_k[torch.arange(B, device=dev), best.clamp(min=0).long()].cpu().numpy()
+    for j, i in enumerate(todo):
+        if best_h[j] < 0:
+            continue
+        a, b = pts[i]
+        status = mask_h[j, :len(a)].reshape(-1, 1).copy()
+        out[i] = (_refit(a, b, H_best[j].reshape(3, 3), status), status)
+    return out
+
+
+def find_homography_ransac(ptsA, ptsB, reproj_thresh, max_iters=RANSAC_MAX_ITERS, seed=RANSAC_SEED):
+    """GPU RANSAC (hypothesis scoring) + host refit on the winner's inliers.
+    Returns ``(H 3x3 float64 | None, status N x 1 uint8 | None)`` like
+    ``cv2.findHomography(ptsA, ptsB, cv2.RANSAC, reproj_thresh)``."""
+    return find_homography_ransac_batch([(ptsA, ptsB)], reproj_thresh, max_iters, seed)[0]
+
+
+def match_keypoints_batch(items, ratio=0.75, reprojThresh=4.0):
+    """``StitcherBase.matchKeypoints`` (reference :405-448) for several image pairs at once - BASELINE config 4's
+    "4 x 1080p pairs": ONE matching launch over all pairs (descriptor sets padded to the longest), one
+    device->host copy of the survivors, ONE RANSAC scoring launch, host refits.
+
+    ``items``: list of ``(kpsA, kpsB, featuresA, featuresB)``, all features of one dtype (uint8 -> Hamming,
+    float32 -> L2).  Returns a list of ``(H, matches, status)``."""
+    dev = _device()
+    feats = [(np.ascontiguousarray(fa), np.ascontiguousarray(fb)) for (_, _, fa, fb) in items]
+    kinds = {f.dtype for pair in feats for f in pair}
+    if len(kinds) != 1 or next(iter(kinds)) not in (np.dtype(np.uint8), np.dtype(np.float32)):
+        raise TypeError("descriptors must all be uint8 (Hamming) or all float32 (L2), got %s" % sorted(map(str, kinds)))
+    dt = next(iter(kinds))
+    B = len(items)
+    D = feats[0][0].shape[1]
+    nq_max = max(len(fa) for fa, _ in feats)
+    nt_max = max(len(fb) for _, fb in feats)
+    hq = np.zeros((B, nq_max, D), dt)
+    ht = np.zeros((B, max(nt_max, 1), D), dt)
+    nq = np.zeros((B,), np.int32)
+    nt = np.zeros((B,), np.int32)
+    for j, (fa, fb) in enumerate(feats):
+        hq[j, :len(fa)] = fa
+        ht[j, :len(fb)] = fb
+        nq[j], nt[j] = len(fa), len(fb)
+    idx2, _dist2, keep = match_top2_batch(torch.from_numpy(hq).to(dev), torch.from_numpy(ht).to(dev),
+                                          torch.from_numpy(nq).to(dev), torch.from_numpy(nt).to(dev), ratio=ratio)
+    packed = torch.where(keep.bool(), idx2[:, :, 0], torch.full_like(idx2[:, :, 0], -1)).cpu().numpy()   # one copy
+    all_matches, point_pairs = [], []
+    for j, (kpsA, kpsB, _, _) in enumerate(items):
+        query = np.nonzero(packed[j, :nq[j]] >= 0)[0]
+        matches = [(int(packed[j, i]), int(i)) for i in query]
+        all_matches.append(matches)
+        if len(matches) > 4:
+            point_pairs.append((np.float32([kpsA[i] for (_, i) in matches]), np.float32([kpsB[i] for (i, _) in matches])))
+        else:
+            point_pairs.append((np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32)))
+    fits = find_homography_ransac_batch(point_pairs, reprojThresh)
+    return [(fits[j][0], all_matches[j], fits[j][1]) for j in range(B)]
 
 
 def match_keypoints(kpsA, kpsB, featuresA, featuresB, ratio=0.75, reprojThresh=4.0):
-    """``StitcherBase.matchKeypoints`` (reference :405-448): returns
-    ``(H, matches, status)``."""
-    featuresA = np.ascontiguousarray(featuresA)
-    featuresB = np.ascontiguousarray(featuresB)
-    if featuresA.dtype != np.uint8 or featuresB.dtype != np.uint8:
-        raise NotImplementedError(
-            "only binary (uint8, e.g. ORB) descriptors are matched on the GPU; float descriptors "
-            "(the reference's SIFT/L2 branch) are outside BASELINE.json's recalibration workload")
-    dev = _device()
-    q = torch.from_numpy(featuresA).to(dev)[None]
-    t = torch.from_numpy(featuresB).to(dev)[None]
-    idx2, _dist2, keep = match_top2_batch(q, t, ratio=ratio)
-    keep_h = keep[0].cpu().numpy().astype(bool)
-    idx_h = idx2[0, :, 0].cpu().numpy()
-    query = np.nonzero(keep_h)[0]
-    matches = [(int(idx_h[i]), int(i)) for i in query]
-    H = None
-    status = None
-    if len(matches) > 4:
-        ptsA = np.float32([kpsA[i] for (_, i) in matches])
-        ptsB = np.float32([kpsB[i] for (i, _) in matches])
-        H, status = find_homography_ransac(ptsA, ptsB, reprojThresh)
-    return H, matches, status
+    """``StitcherBase.matchKeypoints`` (reference :405-448): returns ``(H, matches, status)``.  Binary (uint8)
+    descriptors are matched by Hamming distance, float32 ones (the reference's own SIFT branch) by L2."""
+    return match_keypoints_batch([(kpsA, kpsB, featuresA, featuresB)], ratio, reprojThresh)[0]

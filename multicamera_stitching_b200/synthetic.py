@@ -81,6 +81,29 @@ def homography_from_points(height, width, canvas_width, overlap=0.4):
     return M
 
 
+def synthetic_stitcher(n_cams, h, w, channels=3, super_mode=False, kind="smooth", frame_index=0,
+                       xoffset=0, yoffset=0, use_points_first=False):
+    """A ``Stitcher`` calibrated on the synthetic camera geometry above, stage by stage (each stage's
+    homography depends on the width of the canvas stitched so far, like ``calibrate_stitcher`` calibrates
+    against ``img_result``, reference StitcherClass.py:96-104).
+
+    Returns ``(stitcher, homographies, labels, images_dic)``."""
+    from .StitcherClass import Stitcher
+    images = make_frames(n_cams, h, w, channels, frame_index, kind)
+    st = Stitcher(images, super_mode=super_mode)
+    labels = list(st.img_labels)
+    shapes = [images[l].shape for l in labels]
+    homographies = []
+    shapeB = tuple(shapes[0])
+    for k in range(n_cams - 1):
+        cw = shapeB[1]
+        H = homography_from_points(h, w, cw) if (use_points_first and k == 0) else make_homography(k, h, w, cw)
+        homographies.append(H)
+        st.stitchers[k].set_homography(H, shapeA=shapes[k + 1], shapeB=shapeB, xoffset=xoffset, yoffset=yoffset)
+        shapeB = st.stitchers[k].result_shape()
+    return st, homographies, labels, images
+
+
 # ---------------------------------------------------------------------------
 # recalibration workload (BASELINE.json config 4): feature-rich image pairs
 def make_textured(height, width, seed=0, channels=3):

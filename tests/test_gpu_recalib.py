@@ -204,3 +204,115 @@ def test_calibrate_then_stitch_matches_the_cv2_chain_on_the_same_state(cuda_devi
             state[key] = getattr(sb, key)
     ref = stitcher_ref.stitch_chain([state], list(st.img_labels), images)
     assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+# ---------------------------------------------------------------------------
+# float descriptors / L2: the reference's own matcher branch (StitcherClass.py:380-386, :423-433)
+def sift_like(rng, n, dim=128):
+    """Integer-valued float32 descriptors in 0..255, the form OpenCV's SIFT emits."""
+    return np.minimum(255, rng.gamma(0.6, 40.0, size=(n, dim))).astype(np.uint8).astype(np.float32)
+
+
+def bf_l2(fa, fb, ratio):
+    raw = cv2.BFMatcher(cv2.NORM_L2).knnMatch(fa, fb, 2)
+    idx = -np.ones((len(fa), 2), np.int32)
+    dist = -np.ones((len(fa), 2), np.float32)
+    for i, m in enumerate(raw):
+        for j, mm in enumerate(m[:2]):
+            idx[i, j], dist[i, j] = mm.trainIdx, mm.distance
+    keep = np.array([len(m) == 2 and m[0].distance < m[1].distance * ratio for m in raw], dtype=bool)
+    return idx, dist, keep
+
+
+@pytest.mark.parametrize("nq,nt,dim", [(2000, 2000, 128), (333, 1100, 128), (100, 37, 64), (5, 1, 128), (40, 300, 36)])
+def test_l2_matcher_equals_bfmatcher_on_sift_like_descriptors(cuda_device, nq, nt, dim):
+    rng = np.random.default_rng(nq + 3 * nt)
+    fb = sift_like(rng, nt, dim)
+    fa = sift_like(rng, nq, dim)
+    n_copy = min(nq, nt) // 2
+    fa[:n_copy] = np.clip(fb[rng.permutation(nt)[:n_copy]] + rng.integers(-6, 7, (n_copy, dim)), 0, 255).astype(np.float32)
+    if nt >= 3 and nq >= 2:            # exact ties: equal distance, the lower train index comes first
+        fb[nt - 1] = fb[0]
+        fa[nq - 1] = fb[0]
+    q = torch.from_numpy(fa).to(cuda_device)[None]
+    t = torch.from_numpy(fb).to(cuda_device)[None]
+    idx2, dist2, keep = recalib.match_top2_batch(q, t, ratio=0.75)
+    torch.cuda.synchronize()
+    ridx, rdist, rkeep = bf_l2(fa, fb, 0.75)
+    assert np.array_equal(idx2[0].cpu().numpy(), ridx)
+    assert np.array_equal(dist2[0].cpu().numpy(), rdist)      # sums of squares are exact in float32: bit-identical
+    assert np.array_equal(keep[0].cpu().numpy().astype(bool), rkeep)
+
+
+def test_l2_matcher_general_floats_and_ragged_batch(cuda_device):
+    """Arbitrary float descriptors: the float32 sum may round differently from OpenCV's SIMD order in the last
+    bit, so distances are compared to 1e-5 relative and indices wherever the two best are not that close."""
+    rng = np.random.default_rng(5)
+    sizes = [(400, 500), (1, 3), (0, 10), (30, 0), (257, 129)]
+    fa_list = [rng.normal(0, 1, (a, 128)).astype(np.float32) for a, _ in sizes]
+    fb_list = [rng.normal(0, 1, (b, 128)).astype(np.float32) for _, b in sizes]
+    nq_max, nt_max = max(a for a, _ in sizes), max(b for _, b in sizes)
+    q = torch.zeros((len(sizes), nq_max, 128))
+    t = torch.zeros((len(sizes), nt_max, 128))
+    for i, (fa, fb) in enumerate(zip(fa_list, fb_list)):
+        q[i, :len(fa)] = torch.from_numpy(fa)
+        t[i, :len(fb)] = torch.from_numpy(fb)
+    nq = torch.tensor([a for a, _ in sizes], dtype=torch.int32, device=cuda_device)
+    nt = torch.tensor([b for _, b in sizes], dtype=torch.int32, device=cuda_device)
+    idx2, dist2, keep = recalib.match_top2_batch(q.to(cuda_device), t.to(cuda_device), nq, nt, ratio=0.9)
+    torch.cuda.synchronize()
+    for i, (fa, fb) in enumerate(zip(fa_list, fb_list)):
+        n = len(fa)
+        gi, gd = idx2[i, :n].cpu().numpy(), dist2[i, :n].cpu().numpy()
+        if n == 0:
+            continue
+        if len(fb) == 0:
+            assert (gi == -1).all()
+            continue
+        ridx, rdist, _ = bf_l2(fa, fb, 0.9)
+        assert np.allclose(gd, rdist, rtol=1e-5, atol=0)
+        clear = np.ones(n, bool) if len(fb) < 3 else (rdist[:, 1] - rdist[:, 0]) > 1e-4 * rdist[:, 1]
+        assert np.array_equal(gi[clear, 0], ridx[clear, 0])
+
+
+def test_match_keypoints_float_descriptors_equal_the_cv2_loop(cuda_device):
+    """``StitcherBase.matchKeypoints`` on float (SIFT-like) descriptors - the branch the reference itself runs:
+    the match list equals cv2's loop, the homography agrees through reprojection."""
+    rng = np.random.default_rng(12)
+    nA, nB = 600, 700
+    fb = sift_like(rng, nB)
+    perm = rng.permutation(nB)[:nA]
+    fa = np.clip(fb[perm] + rng.integers(-5, 6, (nA, 128)), 0, 255).astype(np.float32)
+    fa[450:] = sift_like(rng, 150)
+    H_true = np.array([[0.97, 0.02, 310.0], [-0.015, 1.01, 7.5], [1e-5, -2e-5, 1.0]])
+    kpsA = rng.uniform(0, 1900, (nA, 2)).astype(np.float32)
+    proj = np.c_[kpsA, np.ones(nA)] @ H_true.T
+    kpsB = rng.uniform(0, 1900, (nB, 2)).astype(np.float32)
+    kpsB[perm[:450]] = (proj[:450, :2] / proj[:450, 2:]).astype(np.float32) + rng.normal(0, 0.3, (450, 2)).astype(np.float32)
+    H, matches, status = StitcherBase().matchKeypoints(kpsA, kpsB, fa, fb, ratio=0.75, reprojThresh=3.0)
+    Hc, mc, sc = stitcher_ref.match_keypoints(kpsA, kpsB, fa, fb, ratio=0.75, reprojThresh=3.0)
+    assert matches == mc and len(matches) > 400
+    corners = np.float64([[0, 0, 1], [1920, 0, 1], [1920, 1080, 1], [0, 1080, 1]])
+    pa, pb = corners @ H.T, corners @ Hc.T
+    assert np.abs(pa[:, :2] / pa[:, 2:] - pb[:, :2] / pb[:, 2:]).max() < 0.5
+    assert (status.ravel() == sc.ravel()).mean() > 0.98
+
+
+def test_match_keypoints_batch_equals_single_calls(cuda_device):
+    """The batched form (config 4's four pairs in one matching and one RANSAC launch) returns, pair by pair,
+    what the single-pair calls return."""
+    items = []
+    for k in range(4):
+        imageB, imageA, _ = synthetic.make_pair(270, 480, seed=k)
+        sb = StitcherBase()
+        sb.nfeatures = 500
+        kA, fA = sb.detectAndDescribe(imageA)
+        kB, fB = sb.detectAndDescribe(imageB)
+        items.append((kA, kB, fA, fB))
+    batch = recalib.match_keypoints_batch(items, ratio=0.75, reprojThresh=3.0)
+    for item, (H, matches, status) in zip(items, batch):
+        H1, m1, s1 = recalib.match_keypoints(*item, ratio=0.75, reprojThresh=3.0)
+        assert matches == m1
+        assert (H is None) == (H1 is None)
+        if H is not None:
+            assert np.allclose(H, H1) and np.array_equal(status, s1)

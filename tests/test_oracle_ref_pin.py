@@ -225,3 +225,33 @@ def test_reference_pickle_loads_into_the_product_class(ref, tmp_path):
     for sb, ours in zip(rs.stitchers, loaded.stitchers):
         for f in ("cachedAH", "Bpts", "ABSize", "x_limits", "y_limits", "AimgSize", "BimgSize", "super_mode", "sid"):
             assert np.array_equal(np.asarray(getattr(sb, f)), np.asarray(getattr(ours, f))), f
+
+
+# ---- debug overlay (StitcherClass.py:244-245, 450-483) ----------------------------------------------------
+@pytest.mark.parametrize("n,super_mode", [(3, False), (4, True), (5, False)])
+def test_per_stage_overlays_equal_the_reference(ref, n, super_mode):
+    """``Stitcher.stitch(draw_descriptors=True)``: the reference draws at EVERY stage; the product composites
+    once and then puts each stage's overlay where its canvas ended up - same pixels.  (Host code: the panorama
+    under the overlays comes from the oracle here, on the GPU it comes from the kernel.)"""
+    h, w = 120, 200
+    st, states, labels, images = synthetic_chain(n, h, w, 3, super_mode=super_mode, kind="smooth")
+    homs, cw = [], w
+    for k in range(n - 1):
+        homs.append(synthetic.make_homography(k, h, w, cw))
+        cw = st.stitchers[k].result_shape()[1]
+    rs = reference_chain(ref, images, homs, super_mode)
+    want = rs.stitch(images, draw_descriptors=True)
+    base = stitcher_ref.stitch_chain(states, labels, images).copy()
+    for ours, theirs in zip(st.stitchers, rs.stitchers):
+        ours.sid = theirs.sid
+    flat = st.plan.__func__  # noqa: F841  (the plan needs a device; the overlay code only needs the flat layers)
+    from multicamera_stitching_b200 import plan as planmod
+    flat = planmod.flatten_chain(st.stitchers, [images[l].shape for l in labels])
+
+    class _P(object):
+        pass
+    p = _P()
+    p.flat = flat
+    st.plan = lambda shapes, device=None: p
+    got = st._draw_overlays(base, [images[l] for l in labels])
+    assert got.shape == want.shape and np.array_equal(got, want)
