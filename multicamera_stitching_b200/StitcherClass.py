@@ -157,9 +157,17 @@ class Stitcher(Debugger):
             x0, y0, x1, y1 = (int(v) for v in l.rect)
             if x1 <= x0 or y1 <= y0:
                 continue
-            sub = np.ascontiguousarray(out[y0:y1, x0:x1])
-            st.draw_descriptors(sub, offset=(l.ox - x0, l.oy - y0), canvas_size=st.ABSize)
-            out[y0:y1, x0:x1] = sub
+            # draw on the visible part of the stage's canvas plus a margin that is still canvas (anti-aliased text
+            # next to the crop edge takes coverage from glyph parts beyond it; clipping at the canvas edge itself is
+            # what the reference does too)
+            m = 32
+            cw, ch = int(st.ABSize[0]), int(st.ABSize[1])
+            ex0, ey0 = max(x0 - m, l.ox), max(y0 - m, l.oy)
+            ex1, ey1 = min(x1 + m, l.ox + cw), min(y1 + m, l.oy + ch)
+            sub = np.zeros((ey1 - ey0, ex1 - ex0) + out.shape[2:], dtype=out.dtype)
+            sub[y0 - ey0:y1 - ey0, x0 - ex0:x1 - ex0] = out[y0:y1, x0:x1]
+            st._draw_descriptors_at(sub, offset=(l.ox - ex0, l.oy - ey0), canvas_size=st.ABSize)
+            out[y0:y1, x0:x1] = sub[y0 - ey0:y1 - ey0, x0 - ex0:x1 - ex0]
         return out
 
     def stitch_batch(self, frames_dic, out=None):
@@ -378,11 +386,14 @@ class StitcherBase(Debugger):
         from . import recalib
         return recalib.match_keypoints(kpsA, kpsB, featuresA, featuresB, ratio, reprojThresh)
 
-    def draw_descriptors(self, img_src, offset=(0, 0), canvas_size=None):
+    def draw_descriptors(self, img_src):
         """Debug overlay of corners / ROI limits, drawn exactly like the reference's (:450-483, text through
-        Calibration_Utils.print_list_text).  ``offset`` / ``canvas_size`` (extension): draw the overlay of a stage
-        whose canvas origin sits at ``offset`` inside ``img_src`` and whose canvas is ``canvas_size = (w, h)`` -
-        how ``Stitcher.stitch`` puts every stage's overlay into the final panorama."""
+        Calibration_Utils.print_list_text)."""
+        return self._draw_descriptors_at(img_src)
+
+    def _draw_descriptors_at(self, img_src, offset=(0, 0), canvas_size=None):
+        """The overlay of a stage whose canvas origin sits at ``offset`` inside ``img_src`` and whose canvas is
+        ``canvas_size = (w, h)`` - how ``Stitcher.stitch`` puts every stage's overlay into the final panorama."""
         dx, dy = int(offset[0]), int(offset[1])
         cw, ch = (img_src.shape[1], img_src.shape[0]) if canvas_size is None else (int(canvas_size[0]), int(canvas_size[1]))
         white = (255, 255, 255)
