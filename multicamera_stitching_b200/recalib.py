@@ -79,8 +79,22 @@ def ransac_batch(ptsA, ptsB, samples, reproj_thresh, n=None):
     return counts, H_k, best, mask
 
 
+_SAMPLE_CACHE = {}
+
+
 def draw_samples(n_points, k, seed=RANSAC_SEED):
-    """``k`` minimal samples of 4 distinct point indices (host-seeded)."""
+    """``k`` minimal samples of 4 distinct point indices (host-seeded, so deterministic per ``(n_points, k,
+    seed)`` and cached: a rig re-calibrates with about the same number of matches every time)."""
+    key = (int(n_points), int(k), int(seed))
+    hit = _SAMPLE_CACHE.get(key)
+    if hit is None:
+        if len(_SAMPLE_CACHE) > 64:
+            _SAMPLE_CACHE.clear()
+        hit = _SAMPLE_CACHE[key] = _draw_samples(*key)
+    return hit
+
+
+def _draw_samples(n_points, k, seed):
     rng = np.random.default_rng(seed)
     if n_points < 4:
         return np.zeros((k, 4), dtype=np.int32)
@@ -132,54 +146,63 @@ def fit_homography_dlt(a, b):
 
 def refine_homography(H, a, b, iters=REFINE_ITERS):
     """Levenberg-Marquardt on the reprojection error over 8 parameters, the
-    role of OpenCV's HomographyRefineCallback."""
+    role of OpenCV's HomographyRefineCallback.  The Jacobian rows of a point are
+    (x, y, 1, 0, 0, 0, -x u, -y u) / w and (0, 0, 0, x, y, 1, -x v, -y v) / w: they are held as one
+    2n x 8 array that is rebuilt in place per iteration."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     h = (H / H[2, 2]).ravel()[:8].copy()
+    n = len(a)
+    ax, ay, bx, by = a[:, 0], a[:, 1], b[:, 0], b[:, 1]
+    J = np.zeros((2 * n, 8))
+    err = np.empty(2 * n)
 
-    def residual(h8):
-        w = h8[6] * a[:, 0] + h8[7] * a[:, 1] + 1.0
-        x = (h8[0] * a[:, 0] + h8[1] * a[:, 1] + h8[2]) / w
-        y = (h8[3] * a[:, 0] + h8[4] * a[:, 1] + h8[5]) / w
+    def residual(h8, out):
+        w = h8[6] * ax + h8[7] * ay + 1.0
+        x = (h8[0] * ax + h8[1] * ay + h8[2]) / w
+        y = (h8[3] * ax + h8[4] * ay + h8[5]) / w
+        out[:n] = x - bx
+        out[n:] = y - by
         return x, y, w
 
     lam = 1e-3
-    x, y, w = residual(h)
-    err = np.concatenate([x - b[:, 0], y - b[:, 1]])
+    x, y, w = residual(h, err)
     cost = float(err @ err)
+    err2 = np.empty(2 * n)
     for _ in range(iters):
-        n = len(a)
-        J = np.zeros((2 * n, 8))
         iw = 1.0 / w
-        J[:n, 0] = a[:, 0] * iw
-        J[:n, 1] = a[:, 1] * iw
+        xw, yw = ax * iw, ay * iw
+        J[:n, 0] = xw
+        J[:n, 1] = yw
         J[:n, 2] = iw
-        J[:n, 6] = -a[:, 0] * x * iw
-        J[:n, 7] = -a[:, 1] * x * iw
-        J[n:, 3] = a[:, 0] * iw
-        J[n:, 4] = a[:, 1] * iw
+        J[:n, 6] = -xw * x
+        J[:n, 7] = -yw * x
+        J[n:, 3] = xw
+        J[n:, 4] = yw
         J[n:, 5] = iw
-        J[n:, 6] = -a[:, 0] * y * iw
-        J[n:, 7] = -a[:, 1] * y * iw
+        J[n:, 6] = -xw * y
+        J[n:, 7] = -yw * y
         JtJ = J.T @ J
         g = J.T @ err
+        dg = np.diag(np.diag(JtJ))
         improved = False
         for _try in range(6):
             try:
-                step = np.linalg.solve(JtJ + lam * np.diag(np.diag(JtJ)), -g)
+                step = np.linalg.solve(JtJ + lam * dg, -g)
             except np.linalg.LinAlgError:
                 lam *= 10
                 continue
-            x2, y2, w2 = residual(h + step)
-            err2 = np.concatenate([x2 - b[:, 0], y2 - b[:, 1]])
+            x2, y2, w2 = residual(h + step, err2)
             cost2 = float(err2 @ err2)
             if cost2 < cost:
-                h, x, y, w, err, cost = h + step, x2, y2, w2, err2, cost2
+                converged = cost - cost2 <= 1e-9 * cost     # the fit has stopped moving
+                h, x, y, w, cost = h + step, x2, y2, w2, cost2
+                err, err2 = err2, err
                 lam = max(lam * 0.1, 1e-12)
-                improved = True
+                improved = not converged
                 break
             lam *= 10
-        if not improved:
+        if not improved or cost < 1e-18:
             break
     return np.append(h, 1.0).reshape(3, 3)
 
@@ -272,10 +295,11 @@ def match_keypoints_batch(items, ratio=0.75, reprojThresh=4.0):
     all_matches, point_pairs = [], []
     for j, (kpsA, kpsB, _, _) in enumerate(items):
         query = np.nonzero(packed[j, :nq[j]] >= 0)[0]
-        matches = [(int(packed[j, i]), int(i)) for i in query]
+        train = packed[j, query]
+        matches = list(zip(train.tolist(), query.tolist()))     # (trainIdx, queryIdx), reference :428-433
         all_matches.append(matches)
         if len(matches) > 4:
-            point_pairs.append((np.float32([kpsA[i] for (_, i) in matches]), np.float32([kpsB[i] for (i, _) in matches])))
+            point_pairs.append((np.asarray(kpsA, dtype=np.float32)[query], np.asarray(kpsB, dtype=np.float32)[train]))
         else:
             point_pairs.append((np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32)))
     fits = find_homography_ransac_batch(point_pairs, reprojThresh)
