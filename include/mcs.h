@@ -16,7 +16,18 @@
  *     thread;
  *   - work is enqueued on `cuda_stream` (a cudaStream_t, NULL = default
  *     stream) and is asynchronous with respect to the host;
- *   - the library allocates nothing the caller must free except mcs_plan.
+ *   - the library allocates nothing the caller must free except mcs_plan;
+ *   - a plan serves ONE stream at a time: mcs_stitch_u8 keeps per-launch state
+ *     (the run-time work counters of the tiled kernel, scratch for padded rows,
+ *     the cached TMA descriptors) in the plan, so two launches of the same plan
+ *     must be ordered on one stream (or by events).  Different plans are
+ *     independent;
+ *   - bit-exactness with cv2.warpPerspective is guaranteed for layer canvases
+ *     (stage ABSize / prewarp dsize) of at least 16 rows: OpenCV splits shorter
+ *     canvases into blocks wider than the 64 columns the coordinate recipe of
+ *     this library assumes (imgwarp.cpp WarpPerspectiveInvoker: bh0 = min(16,
+ *     rows), bw0 = min(1024 / bh0, cols)), which can move the float64 rounding
+ *     of X0 + M0*x1 by one 1/32-px bucket.
  */
 #ifndef MCS_B200_H
 #define MCS_B200_H

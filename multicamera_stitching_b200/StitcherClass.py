@@ -56,6 +56,10 @@ def _shape_of(img):
 class Stitcher(Debugger):
     """N-camera panorama: a chain of N-1 pairwise stitchers (reference :50-177)."""
 
+    # Class-level default: an object unpickled from a configuration the REFERENCE saved is built without
+    # __init__ and has no blend-mode attribute.
+    feather_log2 = 0
+
     def __init__(self, images_dic, super_mode=False):
         # labels sorted like np.sort(images_dic.keys()) (reference :61)
         self.img_labels = np.sort(list(images_dic.keys()))

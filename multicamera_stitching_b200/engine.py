@@ -179,7 +179,8 @@ class CompositeEngine(object):
 
     def __init__(self, device=None):
         self._device = device
-        self._plans = {}
+        self._plans = {}          # insertion-ordered: least recently used first
+        self.max_plans = 16
         self._staging = {}
 
     @property
@@ -200,13 +201,15 @@ class CompositeEngine(object):
         device = torch.device(device) if device is not None else self.device
         feather_log2 = int(feather_log2 or 0)
         key = (str(device), shapes, sig, feather_log2)
-        if key not in self._plans:
+        if key in self._plans:
+            self._plans[key] = self._plans.pop(key)      # most recently used last
+        else:
             flat = flatten_chain(stages, shapes)
             if feather_log2 and any(_stage_field(st, "super_mode") and _stage_field(st, "cachedAH") is not None
                                     for st in stages):
                 raise PlanUnsupported("the feather blend does not support super_mode crops")
-            if len(self._plans) > 8:
-                self._plans.clear()
+            while len(self._plans) >= self.max_plans:     # evict the least recently used, one at a time
+                self._plans.pop(next(iter(self._plans)))
             self._plans[key] = CompiledPlan(flat, device, feather_log2) if flat is not None else None
         return self._plans[key]
 

@@ -79,14 +79,16 @@ class _OnePlan(object):
     def plan(self, key, shape, device, make_layer, out_wh):
         from .engine import CompiledPlan
         full = (key, tuple(shape), str(device))
-        p = self._plans.get(full)
-        if p is None:
+        p = self._plans.pop(full, None)
+        if p is not None:
+            self._plans[full] = p                        # most recently used last
+        else:
             if len(shape) not in (2, 3):
                 raise ValueError("frames must be H x W or H x W x C, got shape %r" % (tuple(shape),))
             channels = 1 if len(shape) == 2 else int(shape[2])
             flat = FlatPlan([make_layer()], int(out_wh[0]), int(out_wh[1]), channels, len(shape))
-            if len(self._plans) > 16:
-                self._plans.clear()
+            while len(self._plans) >= 16:                # evict the least recently used, one at a time
+                self._plans.pop(next(iter(self._plans)))
             p = CompiledPlan(flat, device)
             self._plans[full] = p
         return p

@@ -176,13 +176,26 @@ def stitch_capture(stitcher, seq, capture=0, lo=0, hi=None, device=None, chunk=1
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     pipe = SequencePipeline(stitcher, shapes, device, chunk=chunk, depth=depth)
     out = pinned_like((b - a,) + pipe.plan.out_shape())
-    bufs = None
-    for s in range(a, b, batch):
-        e = min(b, s + batch)
-        if bufs is None or e - s != batch:
-            bufs = seq.read_batch(capture, s, e, workers=workers)
+    # Decode-ahead (the reference's player replays the next frames while the current ones are being
+    # stitched, video_mapping_node.py:105-130): two sets of pinned decode buffers; while the pipeline
+    # composites batch k from one set, a helper thread decodes batch k + 1 into the other.
+    ranges = [(s, min(b, s + batch)) for s in range(a, b, batch)]
+    sets = [None, None]
+
+    def decode(i):
+        s, e = ranges[i]
+        cur = sets[i & 1]
+        if cur is None or int(next(iter(cur.values())).shape[0]) != e - s:
+            sets[i & 1] = seq.read_batch(capture, s, e, workers=workers)
         else:
-            seq.read_batch(capture, s, e, out=bufs, workers=workers)
-        pipe.run({l: bufs[l] for l in stitcher.img_labels}, out[s - a:e - a])
-        torch.cuda.synchronize(device)   # the decode buffers are reused by the next batch
+            seq.read_batch(capture, s, e, out=cur, workers=workers)
+        return sets[i & 1]
+
+    with ThreadPoolExecutor(max_workers=1) as ahead:
+        pending = ahead.submit(decode, 0)
+        for i, (s, e) in enumerate(ranges):
+            bufs = pending.result()
+            if i + 1 < len(ranges):
+                pending = ahead.submit(decode, i + 1)   # the other buffer set: batch i - 1 has left it (run() blocks)
+            pipe.run({l: bufs[l] for l in stitcher.img_labels}, out[s - a:e - a])
     return a, out

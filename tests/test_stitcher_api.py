@@ -90,6 +90,33 @@ def test_pickle_written_under_reference_module_name_loads(tmp_path):
     assert np.array_equal(loaded.stitchers[0].cachedAH, st.stitchers[0].cachedAH)
 
 
+def test_python2_pickle_fixture_loads():
+    """tests/golden/stitcher_py2.pkl holds the opcode stream CPython 2.7 + numpy write for the reference's
+    save_stitcher (protocol 2, str opcodes, an OBJ and a NEWOBJ instance, numpy arrays with raw byte-string
+    states; scripts/make_py2_pickle.py assembles it by hand).  It must load into this module's classes with
+    str labels, float64 matrices and the class-level defaults the reference's objects never had."""
+    import pickletools
+    path = os.path.join(os.path.dirname(__file__), "golden", "stitcher_py2.pkl")
+    ops = {op.name for op, _, _ in pickletools.genops(open(path, "rb").read())}
+    assert "SHORT_BINSTRING" in ops and "OBJ" in ops and "NEWOBJ" in ops and not ops & {"BINUNICODE", "SHORT_BINUNICODE"}
+    st, _, labels, images = synthetic_chain(3, 72, 128, 3)
+    loaded = Stitcher(images).load_stitcher(path)
+    assert isinstance(loaded, Stitcher) and [str(l) for l in loaded.img_labels] == list(labels)
+    assert all(isinstance(l, str) for l in loaded.img_labels.tolist())
+    assert loaded.stitcher_labels == st.stitcher_labels and loaded.feather_log2 == 0
+    for a, b in zip(loaded.stitchers, st.stitchers):
+        assert isinstance(a, StitcherBase) and isinstance(a.cachedAH, np.ndarray) and a.cachedAH.dtype == np.float64
+        for f in ("cachedAH", "cachedAINVH", "cachedBH", "cachedBINVH"):
+            assert np.array_equal(getattr(a, f), getattr(b, f))
+        assert tuple(a.ABSize) == tuple(b.ABSize) and [tuple(p) for p in a.Bpts] == [tuple(p) for p in b.Bpts]
+        assert tuple(a.BimgSize) == tuple(b.BimgSize) and tuple(a.AimgSize) == tuple(b.AimgSize)
+        assert a.x_limits == b.x_limits and a.y_limits == b.y_limits and a.sid == b.sid
+        assert a.descriptor == "ORB" and a.nfeatures == 2000       # defaults a reference pickle lacks
+    # the loaded chain flattens to the same plan as the one it was written from
+    from multicamera_stitching_b200.plan import stage_signature
+    assert [stage_signature(s) for s in loaded.stitchers] == [stage_signature(s) for s in st.stitchers]
+
+
 def test_reset_clears_every_field():
     st, _, _, _ = synthetic_chain(2, 72, 128, 3)
     s = st.stitchers[0]
