@@ -225,9 +225,11 @@ const char* mcs_plan_tiled_status(const mcs_plan* plan);
  * tiled launch); the persistent grid is this times the SM count.  Diagnostics. */
 int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan);
 
-/* Shape of the tiled variant's work table (diagnostics; host int32 out[8]): tiles in total, FAST
+/* Shape of the tiled variant's work table (diagnostics; host int32 out[12]): tiles in total, FAST
  * (four-pixel group descriptors), WARP (per-pixel descriptors), COPY and ZERO tiles, general
- * passes per FAST tile, bytes of one staged source box, frames per sweep of the table. */
+ * passes per FAST tile, bytes of one staged source box, frames per sweep of the table, BAND tiles
+ * (feather mode: tiles that blend with outer layers), 1 when the seam bands are blended inside the
+ * tiled kernel (no second pass); the rest 0. */
 int mcs_plan_tiled_stats(const mcs_plan* plan, int32_t* out);
 
 /*

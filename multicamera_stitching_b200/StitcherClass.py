@@ -522,7 +522,7 @@ def _composite(engine, stages, frames, batched, out=None, debugger=None, feather
             if on_device:
                 return plan.run(frames, out=out, n_frames=n)
             dev = [None] * len(frames)
-            bands = plan.upload_bands(whole=bool(feather_log2))
+            bands = plan.upload_bands()   # feather mode without the fused band form reports whole frames
             for l in plan.flat.layers:   # only what the panorama can see of each camera crosses PCIe
                 dev[l.cam] = engine.upload(l.cam, frames[l.cam], device, bands[l.cam])
             res = plan.run(dev)

@@ -264,9 +264,10 @@ class Plan(object):
 
     def tiled_stats(self):
         """Work table of the tiled variant: tile counts per class, general passes, box bytes, frame block."""
-        out = np.zeros(8, np.int32)
+        out = np.zeros(12, np.int32)
         check(_lib.mcs_plan_tiled_stats(self._h, out.ctypes.data_as(_c_i32p)), "mcs_plan_tiled_stats")
-        keys = ("tiles", "fast", "warp", "copy", "zero", "fast_passes", "box_bytes", "frame_block")
+        keys = ("tiles", "fast", "warp", "copy", "zero", "fast_passes", "box_bytes", "frame_block", "band",
+                "band_fused")
         return dict(zip(keys, (int(v) for v in out)))
 
     def tiled_status(self):

@@ -38,6 +38,9 @@ void mcs_count_launch(int n);
 struct McsLayer {
     double mi[9];            // inverse homography (layer canvas frame -> source), cv::invert closed form
     int rx0, ry0, rx1, ry1;  // visible rectangle, output coordinates, half open
+    int px0, py0, px1, py1;  // the rectangle as it was PASTED (before any super-mode crop cut it): the feather
+                             // blend measures its distances to these edges; equal to the visible rectangle
+                             // unless mcs_plan_set_paste_rects says otherwise
     int ox, oy;              // origin of the layer's canvas frame in output coordinates
     int src_w, src_h;
     int kind;                // MCS_LAYER_*
@@ -77,7 +80,15 @@ static_assert(sizeof(McsTile) == 32, "McsTile must stay 32 bytes");
 #define MCS_TILE_WARP 2   // fixed-point bilinear resample from the staged source box, one descriptor per pixel
 #define MCS_TILE_FAST 3   // the same resample through the group descriptors (four adjacent pixels per thread share
                           // one source window; pixels that do not fit that template go through a short per-pixel list)
-#define MCS_N_CLASSES 4
+#define MCS_TILE_BAND 4   // feather mode: a resampled tile some of whose pixels blend with one or two outer layers
+                          // (the seam band of a pasted rectangle); per frame it stages one box per layer involved
+#define MCS_N_CLASSES 5
+// The tile table is sorted by descending class; segment s of plan->class_first holds class MCS_N_CLASSES - 1 - s.
+#define MCS_SEG(cls) (MCS_N_CLASSES - 1 - (cls))
+
+// BAND tiles: at most this many outer layers blend into one tile (more -> the plan keeps the two-pass band path)
+#define MCS_BAND_MAX_OVERLAYS 2
+#define MCS_BAND_MAX_LOG2 5   // overlay weights (a + 1 <= 32) travel in 6 bits of the overlay descriptors
 
 // Group ("fast") descriptors of a WARP tile, C == 3 only (mcs_tiles.cu builds them, mcs_stitch_tiled.cu reads them).
 // One record per tile: [McsTile, 32 B][general-list length of each warp, 8 x u8][pad to 64 B]
@@ -144,8 +155,17 @@ struct mcs_plan {
     // Work split of the tiled kernel: the CTAs claim chunks (a tile for one block of frames) at run time from
     // d_work[0]; d_work[1] counts finished CTAs and the last one rewinds both, so a plan serves ONE launch at a
     // time (one stream), see mcs.h.
-    int class_first[MCS_N_CLASSES + 1];   // the tile table is sorted FAST, WARP, COPY, ZERO: first tile of each
-                             // class, then n_tiles
+    int class_first[MCS_N_CLASSES + 1];   // the tile table is sorted BAND, FAST, WARP, COPY, ZERO: first tile of
+                             // each class, then n_tiles
+    // feather mode, fused form (mcs_tiles.cu): BAND tiles are the first n_band tiles of the table
+    int band_fused;          // the tiled kernel blends the seam bands itself (no second pass)
+    int n_band;
+    int band_max_ov;         // most outer layers any BAND tile blends with (sizes the kernel's overlay buffer)
+    int4* d_band_issue;      // [n_band][1 + MCS_BAND_MAX_OVERLAYS] {layer, bx, by, box bytes | n_overlays << 24}
+    uint32_t* d_band_desc;   // [n_band][MCS_BAND_MAX_OVERLAYS][2048] overlay descriptors: per-pixel descriptor of the
+                             // outer layer | weight of the value so far << 26 (0 = pixel not blended with this layer)
+    uint8_t* d_wmap[MCS_MAX_LAYERS];   // per layer k >= 1: weight map of the paste of stage k (over the pasted
+                             // rectangle of layer k - 1, values 0 .. 2^feather_log2), nullptr = the distance ramp
     unsigned* d_work;
 };
 

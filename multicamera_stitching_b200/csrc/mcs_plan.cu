@@ -133,6 +133,7 @@ extern "C" int mcs_plan_create_maps(mcs_plan** out, int n_layers, int channels,
         if (x1 < x0) x1 = x0;
         if (y1 < y0) y1 = y0;
         L.rx0 = x0; L.ry0 = y0; L.rx1 = x1; L.ry1 = y1;
+        L.px0 = rect_xyxy[4 * k]; L.py0 = rect_xyxy[4 * k + 1]; L.px1 = rect_xyxy[4 * k + 2]; L.py1 = rect_xyxy[4 * k + 3];
         bool ok = (L.kind == MCS_LAYER_COPY || L.kind == MCS_LAYER_WARP || L.kind == MCS_LAYER_REMAP) && L.src_h > 0 &&
                   L.src_w > 0 && L.src_h < 32767 && L.src_w < 32767;  // cv2.remap's short-coordinate limit
         // canvas-frame coordinates (x - ox, y - oy) must be non-negative inside the rectangle:
@@ -230,7 +231,7 @@ extern "C" int mcs_plan_source_windows(const mcs_plan* plan, int32_t* xyxy) {
     MCS_CHECK_ARG(plan != nullptr && xyxy != nullptr, "mcs_plan_source_windows: NULL argument");
     // The feather band samples outer cameras inside the pasted rectangles, i.e. outside the
     // pixels they own: there every frame counts in full.
-    const bool known = plan->src_win_valid && plan->feather_log2 == 0;
+    const bool known = plan->src_win_valid && (plan->feather_log2 == 0 || plan->band_fused);
     for (int k = 0; k < plan->n_layers; ++k) {
         xyxy[4 * k + 0] = known ? plan->src_win[k][0] : 0;
         xyxy[4 * k + 1] = known ? plan->src_win[k][1] : 0;
@@ -247,7 +248,7 @@ extern "C" int mcs_plan_source_spans(const mcs_plan* plan, int layer, int band_r
     const McsLayer& L = plan->layers[layer];
     const int n_bands = (L.src_h + band_rows - 1) / band_rows;
     const int* span = plan->h_row_span[layer];
-    const bool known = plan->src_win_valid && plan->feather_log2 == 0 && span != nullptr;
+    const bool known = plan->src_win_valid && (plan->feather_log2 == 0 || plan->band_fused) && span != nullptr;
     for (int b = 0; b < n_bands; ++b) {
         int x0 = known ? INT_MAX : 0, x1 = known ? INT_MIN : L.src_w;
         for (int r = b * band_rows; known && r < (b + 1) * band_rows && r < L.src_h; ++r) {
@@ -313,10 +314,12 @@ extern "C" int mcs_plan_tiled_ctas_per_sm(const mcs_plan* plan) { return plan ? 
 
 extern "C" int mcs_plan_tiled_stats(const mcs_plan* plan, int32_t* out) {
     MCS_CHECK_ARG(plan != nullptr && out != nullptr, "mcs_plan_tiled_stats: NULL argument");
-    for (int i = 0; i < 8; ++i) out[i] = 0;
+    for (int i = 0; i < 12; ++i) out[i] = 0;
     if (!plan->tiled_ok) return MCS_OK;
     out[0] = plan->n_tiles;
-    for (int c = 0; c < MCS_N_CLASSES; ++c) out[1 + c] = plan->class_first[c + 1] - plan->class_first[c];
+    for (int c = 1; c < MCS_N_CLASSES; ++c) out[c] = plan->class_first[c + 1] - plan->class_first[c];
+    out[8] = plan->class_first[1] - plan->class_first[0];
+    out[9] = plan->band_fused;
     out[5] = plan->fast_passes;
     out[6] = plan->box_bytes;
     out[7] = plan->frame_block;
@@ -333,13 +336,25 @@ static void free_strips(mcs_plan* plan) {
     plan->strip_pixels = 0;
 }
 
+// The tile table depends on the blend mode (feather mode adds BAND tiles and their boxes).
+static void rebuild_tiles(mcs_plan* plan) {
+    mcs_plan_free_tiles(plan);
+    plan->cache_valid = 0;        // TMA descriptors carry the box sizes
+    plan->grid_ctas_per_sm = 0;   // and the kernel's shared-memory footprint changes
+    mcs_plan_build_tiles(plan);
+}
+
 extern "C" int mcs_plan_set_feather(mcs_plan* plan, int feather_log2) {
     MCS_CHECK_ARG(plan != nullptr, "mcs_plan_set_feather: plan is NULL");
     MCS_CHECK_ARG(feather_log2 >= 0 && feather_log2 <= 12, "mcs_plan_set_feather: feather_log2=%d outside 0..12",
                   feather_log2);
     free_strips(plan);
+    const bool had = plan->feather_log2 > 0;
     plan->feather_log2 = 0;
-    if (feather_log2 == 0) return MCS_OK;
+    if (feather_log2 == 0) {
+        if (had) rebuild_tiles(plan);
+        return MCS_OK;
+    }
     // the blend walks the nested rectangles: they must be nested
     for (int k = 1; k < plan->n_layers; ++k) {
         const McsLayer& o = plan->layers[k];
@@ -393,5 +408,6 @@ extern "C" int mcs_plan_set_feather(mcs_plan* plan, int feather_log2) {
     }
     plan->feather_log2 = feather_log2;
     mcs_feather_build_table(plan);
+    rebuild_tiles(plan);   // the tile table knows the seam bands (BAND tiles): the tiled kernel then blends them itself
     return MCS_OK;
 }

@@ -199,7 +199,7 @@ __device__ __forceinline__ void feather_pixel(const StitchArgs& a, int frame, in
     sample_layer<C>(a.L[m], frame, x, y, v);
     for (int k = m + 1; k < a.n_layers; ++k) {
         const McsLayer& in = a.L[k - 1].g;   // the rectangle pasted at stage k
-        const int d = min(min(x - in.rx0, in.rx1 - 1 - x), min(y - in.ry0, in.ry1 - 1 - y)) + 1;
+        const int d = min(min(x - in.px0, in.px1 - 1 - x), min(y - in.py0, in.py1 - 1 - y)) + 1;
         if (d >= F) break;
         int w[C];
         if (sample_layer<C>(a.L[k], frame, x, y, w)) {
@@ -275,7 +275,7 @@ mcs_feather_table_kernel(const __grid_constant__ StitchArgs a, const int4* __res
             int d = F;
             if (k > m) {
                 const McsLayer& in = a.L[k - 1].g;   // the rectangle pasted at stage k
-                d = min(min(x - in.rx0, in.rx1 - 1 - x), min(y - in.ry0, in.ry1 - 1 - y)) + 1;
+                d = min(min(x - in.px0, in.px1 - 1 - x), min(y - in.py0, in.py1 - 1 - y)) + 1;
                 if (d >= F) break;
             }
             const int xl = x - g.ox, yl = y - g.oy;
@@ -411,6 +411,10 @@ extern "C" int mcs_stitch_u8(const mcs_plan* plan_c, const uint8_t* const* src,
                   dst_frame_stride);
         MCS_CHECK_CUDA(launch_gather<false>(plan, a, nullptr, stream));
         plan->last_variant = 1;
+    }
+    if (plan->feather_log2 > 0 && plan->band_fused && plan->last_variant == 2) {
+        plan->last_variant = 4;   // the tiled kernel blended the seam bands itself (BAND tiles)
+        return MCS_OK;
     }
     if (plan->feather_log2 > 0 && plan->n_strips > 0) {
         // feather blend: the pass above composited with the reference's overwrite; now the seam bands

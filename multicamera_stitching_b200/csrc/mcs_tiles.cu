@@ -193,6 +193,115 @@ mcs_tile_fast_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restri
     }
 }
 
+
+// ---- feather mode: seam bands ------------------------------------------------------------------
+// Specification: oracle/feather_model.py.  At stage k the running canvas (layers 0 .. k-1) is pasted over the
+// warp of layer k; inside the pasted rectangle (that of layer k-1) the two are blended where the weight
+// a = weight of the canvas so far is below F = 2^feather_log2 and layer k's warp touches its source:
+//   value = (a * value + (F - a) * sample_k + F/2) >> feather_log2
+// a comes from the stage's weight map when one was given, else from the distance ramp min(F, 1 + distance to the
+// nearest edge of the pasted rectangle).
+struct BandMaps {
+    const uint8_t* wmap[MCS_MAX_LAYERS];
+};
+
+__device__ __forceinline__ int band_weight(const McsLayer* __restrict__ layers, const BandMaps& maps, int k, int x,
+                                           int y, int F) {
+    const McsLayer& in = layers[k - 1];   // the rectangle pasted at stage k
+    if (maps.wmap[k]) return min(F, (int)__ldg(maps.wmap[k] + (size_t)(y - in.py0) * (in.px1 - in.px0) + (x - in.px0)));
+    return min(F, min(min(x - in.px0, in.px1 - 1 - x), min(y - in.py0, in.py1 - 1 - y)) + 1);
+}
+
+// One warp per (tile, outer layer k): bounding box of the source pixels of layer k that the tile's blended
+// pixels sample (as mcs_tile_bounds_kernel); touched = the tile has such pixels.
+__global__ void __launch_bounds__(256)
+mcs_band_bounds_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restrict__ layers, int n_tiles,
+                       int n_layers, int F, const __grid_constant__ BandMaps maps, TileBounds* __restrict__ out) {
+    const int job = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (job >= n_tiles * n_layers) return;
+    const int t = job / n_layers, k = job - t * n_layers;
+    const McsTile tile = tiles[t];
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN, touched = 0;
+    bool live = tile.layer >= 0 && k > tile.layer;
+    if (live && !maps.wmap[k]) {   // ramp: the tile must come within F - 1 pixels of an edge of the pasted rectangle
+        const McsLayer& in = layers[k - 1];
+        const int x0 = tile.cx0 + tile.c0, x1 = tile.cx0 + tile.c1, y0 = tile.y0, y1 = tile.y0 + tile.h;
+        live = x0 < in.px0 + F - 1 || x1 > in.px1 - (F - 1) || y0 < in.py0 + F - 1 || y1 > in.py1 - (F - 1);
+    }
+    if (live) {
+        const McsLayer& L = layers[k];
+        const int w = tile.c1 - tile.c0;
+        const int n = w * tile.h;
+        for (int i = lane; i < n; i += 32) {
+            const int r = i / w, c = tile.c0 + (i - r * w);
+            const int x = tile.cx0 + c, y = tile.y0 + r;
+            if (band_weight(layers, maps, k, x, y, F) >= F) continue;
+            int X, Y;
+            layer_coords(L, x - L.ox, y - L.oy, X, Y);
+            const int rsx = sat16(X >> 5), rsy = sat16(Y >> 5);
+            const bool in = ((unsigned)rsx < (unsigned)L.src_w || (unsigned)(rsx + 1) < (unsigned)L.src_w) &&
+                            ((unsigned)rsy < (unsigned)L.src_h || (unsigned)(rsy + 1) < (unsigned)L.src_h);
+            if (!in) continue;
+            touched = 1;
+            const int sx = max(-2, min(L.src_w, rsx)), sy = max(-2, min(L.src_h, rsy));
+            mnx = min(mnx, sx); mxx = max(mxx, sx);
+            mny = min(mny, sy); mxy = max(mxy, sy);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, off));
+        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, off));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, off));
+        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, off));
+        touched |= __shfl_xor_sync(0xffffffffu, touched, off);
+    }
+    if (lane == 0) {
+        TileBounds b;
+        b.min_sx = mnx; b.max_sx = mxx; b.min_sy = mny; b.max_sy = mxy; b.touched = touched;
+        b.clamped = 0;
+        b.pad[0] = b.pad[1] = 0;
+        out[job] = b;
+    }
+}
+
+// One CTA per (BAND tile, overlay slot): the overlay descriptors of the tile's 128 x 16 pixel slots in the
+// order of mcs_tile_desc_kernel:  per-pixel descriptor of the outer layer (offset inside ITS staged box, ax,
+// ay) | (a + 1) << 26, or 0 where the pixel does not blend with that layer.
+__global__ void __launch_bounds__(32 * MCS_TILED_WARPS)
+mcs_band_desc_kernel(const McsTile* __restrict__ tiles, const McsLayer* __restrict__ layers, int channels, int F,
+                     const __grid_constant__ BandMaps maps, const int4* __restrict__ band_issue,
+                     uint32_t* __restrict__ desc) {
+    const int t = blockIdx.x / MCS_BAND_MAX_OVERLAYS, o = blockIdx.x - t * MCS_BAND_MAX_OVERLAYS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const McsTile tile = tiles[t];
+    const int4 rec = band_issue[t * (1 + MCS_BAND_MAX_OVERLAYS) + 1 + o];
+    const int k = rec.x;
+    for (int j = 0; j < 8; ++j) {
+        const int row = warp + MCS_TILED_WARPS * (j >> 2), col = lane + 32 * (j & 3);
+        uint32_t w = 0;
+        if (k >= 0 && col >= tile.c0 && col < tile.c1 && row < tile.h) {
+            const McsLayer& L = layers[k];
+            const int x = tile.cx0 + col, y = tile.y0 + row;
+            const int a = band_weight(layers, maps, k, x, y, F);
+            if (a < F) {
+                int X, Y;
+                layer_coords(L, x - L.ox, y - L.oy, X, Y);
+                const int rsx = sat16(X >> 5), rsy = sat16(Y >> 5);
+                const bool in = ((unsigned)rsx < (unsigned)L.src_w || (unsigned)(rsx + 1) < (unsigned)L.src_w) &&
+                                ((unsigned)rsy < (unsigned)L.src_h || (unsigned)(rsy + 1) < (unsigned)L.src_h);
+                if (in) {
+                    const int sx = max(-2, min(L.src_w, rsx)), sy = max(-2, min(L.src_h, rsy));
+                    const int b = (sy - rec.z) * (L.bw4 * 4) + sx * channels - 4 * rec.y;
+                    w = (uint32_t)b | ((uint32_t)(X & 31) << 16) | ((uint32_t)(Y & 31) << 21) | ((uint32_t)(a + 1) << 26);
+                }
+            }
+        }
+        desc[((size_t)t * MCS_BAND_MAX_OVERLAYS + o) * (MCS_CELL_W * MCS_CELL_H) + (j * MCS_TILED_WARPS + warp) * 32 + lane] = w;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -251,8 +360,15 @@ void mcs_plan_free_tiles(mcs_plan* plan) {
     if (plan->d_work) cudaFree(plan->d_work);
     if (plan->d_desc) cudaFree(plan->d_desc);
     if (plan->d_fast) cudaFree(plan->d_fast);
+    if (plan->d_band_issue) cudaFree(plan->d_band_issue);
+    if (plan->d_band_desc) cudaFree(plan->d_band_desc);
     plan->d_desc = nullptr;
     plan->d_fast = nullptr;
+    plan->d_band_issue = nullptr;
+    plan->d_band_desc = nullptr;
+    plan->band_fused = 0;
+    plan->n_band = 0;
+    plan->band_max_ov = 0;
     for (int k = 0; k < MCS_MAX_LAYERS; ++k) {
         free(plan->h_row_span[k]);
         plan->h_row_span[k] = nullptr;
@@ -274,6 +390,7 @@ static int tile_cost(const McsTile& t, int fast_passes) {
     for (int g = 0; g < 4; ++g)
         if (32 * g < t.c1 && 32 * g + 32 > t.c0) ++groups;
     const int px = groups * (t.h > MCS_TILED_WARPS ? 2 : 1);     // pixels per thread of the busiest warp
+    if (t.cls == MCS_TILE_BAND) return 63 + 26 * px + 60 * fast_passes;   // fast_passes = overlays here
     return 63 + 26 * px;
 }
 
@@ -345,6 +462,51 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         return;
     }
 
+    // feather mode: which tiles blend with which outer layers (at most MCS_BAND_MAX_OVERLAYS per tile, else
+    // the plan keeps the two-pass band path of mcs_stitch.cu)
+    struct BandInfo {
+        int n;
+        int layer[MCS_BAND_MAX_OVERLAYS], bx[MCS_BAND_MAX_OVERLAYS], by[MCS_BAND_MAX_OVERLAYS];
+        TileBounds b[MCS_BAND_MAX_OVERLAYS];
+    };
+    std::vector<BandInfo> binfo(n_tiles);
+    memset(binfo.data(), 0, sizeof(BandInfo) * n_tiles);
+    const int F = 1 << plan->feather_log2;
+    BandMaps maps;
+    for (int k = 0; k < MCS_MAX_LAYERS; ++k) maps.wmap[k] = plan->d_wmap[k];
+    bool fused = false;
+    {
+        const char* env = getenv("MCS_TILED_BAND");   // "0": keep the two-pass band path (tests, experiments)
+        const bool want = plan->feather_log2 > 0 && plan->feather_log2 <= MCS_BAND_MAX_LOG2 && plan->n_layers > 1 &&
+                          !(env && atoi(env) == 0);
+        if (want) {
+            const size_t n_jobs = (size_t)n_tiles * plan->n_layers;
+            std::vector<TileBounds> bb(n_jobs);
+            TileBounds* d_bb = nullptr;
+            e = cudaMalloc(&d_bb, sizeof(TileBounds) * n_jobs);
+            if (e == cudaSuccess) {
+                mcs_band_bounds_kernel<<<(unsigned)((n_jobs + 7) / 8), 256>>>(d_tiles, d_layers, n_tiles, plan->n_layers, F,
+                                                                              maps, d_bb);
+                mcs_count_launch(1);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpy(bb.data(), d_bb, sizeof(TileBounds) * n_jobs, cudaMemcpyDeviceToHost);
+            if (d_bb) cudaFree(d_bb);
+            fused = e == cudaSuccess;
+            for (int i = 0; fused && i < n_tiles; ++i)
+                for (int k = 1; fused && k < plan->n_layers; ++k) {
+                    const TileBounds& b = bb[(size_t)i * plan->n_layers + k];
+                    if (!b.touched) continue;
+                    if (binfo[i].n == MCS_BAND_MAX_OVERLAYS) { fused = false; break; }
+                    binfo[i].layer[binfo[i].n] = k;
+                    binfo[i].b[binfo[i].n] = b;
+                    ++binfo[i].n;
+                }
+            if (!fused) memset(binfo.data(), 0, sizeof(BandInfo) * n_tiles);
+            e = cudaSuccess;   // a failed analysis only costs the fused form
+        }
+    }
+
     // classify, place the boxes, size them per layer
     int bw4[MCS_MAX_LAYERS], bh[MCS_MAX_LAYERS];
     int win[MCS_MAX_LAYERS][4];   // source pixels the owned tiles of a layer read: x0, y0, x1, y1
@@ -371,7 +533,34 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         if (t.layer < 0) continue;
         const McsLayer& L = plan->layers[t.layer];
         int need_w = 0, need_h = 0;
-        if (t.cls == MCS_TILE_COPY) {
+        const bool is_band = binfo[i].n > 0;
+        if (is_band) {
+            // a BAND tile resamples its owner through per-pixel descriptors (a COPY owner too: taps with
+            // ax = ay = 0) and stages one more box per outer layer it blends with
+            TileBounds b = bounds[i];
+            if (t.cls == MCS_TILE_COPY) {
+                b.min_sx = t.cx0 + t.c0 - L.ox; b.max_sx = t.cx0 + t.c1 - 1 - L.ox;
+                b.min_sy = t.y0 - L.oy;         b.max_sy = t.y0 + t.h - 1 - L.oy;
+            }
+            t.cls = MCS_TILE_BAND;
+            t.bx = 4 * floor_div(b.min_sx * C, 16);
+            t.by = b.min_sy;
+            need_w = ((b.max_sx + 2) * C + 3) / 4 - t.bx + 1;
+            need_h = b.max_sy + 2 - b.min_sy;
+            grow(t.layer, std::max(0, b.min_sx), std::max(0, b.min_sy), std::min(L.src_w, b.max_sx + 2),
+                 std::min(L.src_h, b.max_sy + 2));
+            for (int o = 0; o < binfo[i].n; ++o) {
+                const int k = binfo[i].layer[o];
+                const McsLayer& K = plan->layers[k];
+                const TileBounds& ob = binfo[i].b[o];
+                binfo[i].bx[o] = 4 * floor_div(ob.min_sx * C, 16);
+                binfo[i].by[o] = ob.min_sy;
+                bw4[k] = std::max(bw4[k], ((ob.max_sx + 2) * C + 3) / 4 - binfo[i].bx[o] + 1);
+                bh[k] = std::max(bh[k], ob.max_sy + 2 - ob.min_sy);
+                grow(k, std::max(0, ob.min_sx), std::max(0, ob.min_sy), std::min(K.src_w, ob.max_sx + 2),
+                     std::min(K.src_h, ob.max_sy + 2));
+            }
+        } else if (t.cls == MCS_TILE_COPY) {
             const int first_byte = (t.cx0 + t.c0 - L.ox) * C, end_byte = (t.cx0 + t.c1 - L.ox) * C;
             t.bx = 4 * floor_div(first_byte, 16);   // TMA: the box must start on a 16-byte boundary
             t.by = t.y0 - L.oy;
@@ -414,8 +603,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         plan->layers[k].bh = bh[k];
         box_bytes = std::max(box_bytes, bw4[k] * 4 * bh[k]);
     }
-    for (int i = 0; i < n_tiles; ++i)   // bytes the TMA delivers for the tile (mbarrier transaction count)
-        if (tiles[i].layer >= 0) tiles[i].reserved = bw4[tiles[i].layer] * 4 * bh[tiles[i].layer];
+    for (int i = 0; i < n_tiles; ++i) tiles[i].reserved = i;   // the tile's index in `binfo` through the sorts below
     // Work split: tiles grouped by class (each class keeps its layer / row / column order, so a
     // CTA's range covers neighbouring cells), costs prefix-summed for the launch-time cut.
     // Inside a class the tiles run in bands of $MCS_TILED_ORDER cell rows over the whole panorama width; inside a band
@@ -439,8 +627,10 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
     // FAST class (C == 3): WARP tiles whose pixels fit the four-pixel group template but for a short
     // per-warp list.  Analysis pass first (list lengths only), then the records once the table has
     // its final order.
+    int first_warp = 0;   // BAND tiles come first
+    while (first_warp < n_tiles && tiles[first_warp].cls == MCS_TILE_BAND) ++first_warp;
     int n_warp_tiles = 0;
-    while (n_warp_tiles < n_tiles && tiles[n_warp_tiles].cls == MCS_TILE_WARP) ++n_warp_tiles;
+    while (first_warp + n_warp_tiles < n_tiles && tiles[first_warp + n_warp_tiles].cls == MCS_TILE_WARP) ++n_warp_tiles;
     std::vector<uint8_t> tile_passes(n_tiles, 0);
     int fast_passes = 0, n_fast = 0;
     {
@@ -451,7 +641,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             std::vector<uint8_t> counts(8 * (size_t)n_warp_tiles);
             e = cudaMalloc(&d_counts, counts.size());
             if (e == cudaSuccess) {
-                mcs_tile_fast_kernel<<<n_warp_tiles, 256>>>(d_tiles, d_layers, n_warp_tiles, nullptr, 0, 0, d_counts);
+                mcs_tile_fast_kernel<<<n_warp_tiles, 256>>>(d_tiles + first_warp, d_layers, n_warp_tiles, nullptr, 0, 0, d_counts);
                 mcs_count_launch(1);
                 e = cudaGetLastError();
             }
@@ -471,18 +661,35 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
                     int mx = 0;
                     for (int w = 0; w < 8; ++w) mx = std::max(mx, (int)counts[8 * (size_t)i + w]);
                     if (mx > limit) continue;
-                    tiles[i].cls = MCS_TILE_FAST;
-                    tiles[i].flags = (short)((mx + 31) / 32);   // carried through the sort, then replaced by the cost
+                    tiles[first_warp + i].cls = MCS_TILE_FAST;
+                    tiles[first_warp + i].flags = (short)((mx + 31) / 32);   // carried through the sort, then replaced by the cost
                     ++n_fast;
                 }
                 if (n_fast > 0) {
                     std::stable_sort(tiles.begin(), tiles.end(), by_class);
-                    for (int i = 0; i < n_fast; ++i) {
+                    for (int i = first_warp; i < first_warp + n_fast; ++i) {
                         tile_passes[i] = (uint8_t)tiles[i].flags;
                         fast_passes = std::max(fast_passes, (int)tiles[i].flags);
                     }
                 }
             }
+        }
+    }
+    // the sorts are done: band records in table order, then the staged bytes of every tile (mbarrier transaction count)
+    const int n_band = first_warp;
+    std::vector<int4> band_issue((size_t)n_band * (1 + MCS_BAND_MAX_OVERLAYS));
+    for (int i = 0; i < n_tiles; ++i) {
+        McsTile& t = tiles[i];
+        const BandInfo bi = binfo[t.reserved];
+        t.reserved = t.layer >= 0 ? bw4[t.layer] * 4 * bh[t.layer] : 0;
+        if (i < n_band) {
+            tile_passes[i] = (uint8_t)bi.n;
+            t.reserved |= bi.n << 24;   // the tile record and the issue record carry the number of overlays
+            int4* r = &band_issue[(size_t)i * (1 + MCS_BAND_MAX_OVERLAYS)];
+            r[0] = make_int4(t.layer, t.bx, t.by, t.reserved);
+            for (int o = 0; o < MCS_BAND_MAX_OVERLAYS; ++o)
+                r[1 + o] = o < bi.n ? make_int4(bi.layer[o], bi.bx[o], bi.by[o], bw4[bi.layer[o]] * 4 * bh[bi.layer[o]])
+                                    : make_int4(-1, 0, 0, 0);
         }
     }
     for (int i = 0; i < n_tiles; ++i) tiles[i].flags = (short)tile_cost(tiles[i], tile_passes[i]);
@@ -507,7 +714,22 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
     uint32_t* d_desc = nullptr;
     uint8_t* d_fast = nullptr;
     const int fast_stride = MCS_FAST_HEADER_BYTES + MCS_FAST_GROUP_BYTES + fast_passes * MCS_FAST_PASS_BYTES;
-    n_warp_tiles = plan->class_first[2];
+    n_warp_tiles = plan->class_first[MCS_SEG(MCS_TILE_COPY)];   // BAND, FAST and WARP tiles
+    int4* d_band_issue = nullptr;
+    uint32_t* d_band_desc = nullptr;
+    if (e == cudaSuccess && n_band > 0) {
+        e = cudaMalloc(&d_band_issue, sizeof(int4) * band_issue.size());
+        if (e == cudaSuccess)
+            e = cudaMemcpy(d_band_issue, band_issue.data(), sizeof(int4) * band_issue.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaMalloc(&d_band_desc, sizeof(uint32_t) * MCS_CELL_W * MCS_CELL_H * MCS_BAND_MAX_OVERLAYS * (size_t)n_band);
+        if (e == cudaSuccess) {
+            mcs_band_desc_kernel<<<n_band * MCS_BAND_MAX_OVERLAYS, 32 * MCS_TILED_WARPS>>>(d_tiles, d_layers, C, F, maps,
+                                                                                          d_band_issue, d_band_desc);
+            mcs_count_launch(1);
+            e = cudaGetLastError();
+        }
+    }
     if (e == cudaSuccess && n_warp_tiles > 0) {
         e = cudaMalloc(&d_desc, sizeof(uint32_t) * MCS_CELL_W * MCS_CELL_H * (size_t)n_warp_tiles);
         if (e == cudaSuccess) {
@@ -518,7 +740,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         if (e == cudaSuccess && n_fast > 0) {
             e = cudaMalloc(&d_fast, (size_t)fast_stride * n_fast);
             if (e == cudaSuccess) {
-                mcs_tile_fast_kernel<<<n_fast, 256>>>(d_tiles, d_layers, n_fast, d_fast, fast_stride, fast_passes, nullptr);
+                mcs_tile_fast_kernel<<<n_fast, 256>>>(d_tiles + n_band, d_layers, n_fast, d_fast, fast_stride, fast_passes, nullptr);
                 mcs_count_launch(1);
                 e = cudaGetLastError();
             }
@@ -533,8 +755,16 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         if (d_desc) cudaFree(d_desc);
         if (d_fast) cudaFree(d_fast);
         if (d_issue) cudaFree(d_issue);
+        if (d_band_issue) cudaFree(d_band_issue);
+        if (d_band_desc) cudaFree(d_band_desc);
         return;
     }
+    plan->d_band_issue = d_band_issue;
+    plan->d_band_desc = d_band_desc;
+    plan->n_band = n_band;
+    plan->band_max_ov = 0;
+    for (int i = 0; i < n_band; ++i) plan->band_max_ov = std::max(plan->band_max_ov, (int)tile_passes[i]);
+    plan->band_fused = fused ? 1 : 0;
     plan->d_issue = d_issue;
     plan->d_fast = d_fast;
     plan->fast_stride = fast_stride;

@@ -48,7 +48,10 @@ def test_feather_kernel_matches_specification(cuda_device, n, h, w, c, log2):
     assert got.shape == ref.shape
     assert np.array_equal(got, ref), int(np.abs(got.astype(int) - ref.astype(int)).max())
     plan = st.plan([images[l].shape for l in labels], cuda_device)
-    assert plan.handle.last_variant() == 3
+    # one launch: the seam bands are BAND tiles of the tiled kernel (variant 4), blended in registers
+    stats = plan.handle.tiled_stats()
+    assert stats["band_fused"] == 1 and stats["band"] > 0, stats
+    assert plan.handle.last_variant() == 4
     # batched, device-resident
     sets = [synthetic_chain(n, h, w, c, kind="noise", frame_index=f)[3] for f in range(3)]
     batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
@@ -58,6 +61,57 @@ def test_feather_kernel_matches_specification(cuda_device, n, h, w, c, log2):
     # width one = the reference's overwrite through the regular kernels
     st.feather_log2 = 0
     assert np.array_equal(st.stitch(images), stitcher_ref.stitch_chain(states, labels, images))
+
+
+@pytest.mark.gpu
+def test_feather_fused_launch_count_and_window_uploads(cuda_device):
+    """The fused form is ONE kernel launch per call, and it keeps the visible-window uploads: the source windows
+    the plan reports cover what the band samples read (a frame poisoned outside them gives the same panorama)."""
+    import torch
+    from multicamera_stitching_b200 import _cabi
+    n, h, w, c, log2 = 4, 180, 320, 3, 3
+    st, states, labels, images = synthetic_chain(n, h, w, c, kind="noise")
+    st.feather_log2 = log2
+    ref = feather_model.feather_chain(states, labels, images, log2)
+    assert np.array_equal(st.stitch(images), ref)
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    batch = {l: torch.from_numpy(images[l][None]).to(cuda_device) for l in labels}
+    before = _cabi.launch_count()
+    st.stitch_batch(batch)
+    assert _cabi.launch_count() - before == 1
+    bands = plan.upload_bands()
+    poisoned = {}
+    some_hidden = False
+    for k, l in enumerate(labels):
+        row, rows, copies = bands[k]
+        keep = np.zeros((rows, row), bool)
+        for cp in copies:
+            keep[cp["y0"]:cp["y0"] + cp["rows"], cp["b0"]:cp["b0"] + cp["nbytes"]] = True
+        some_hidden |= not keep.all()
+        flat = images[l].reshape(rows, row).copy()
+        flat[~keep] = 255 - flat[~keep]
+        poisoned[l] = torch.from_numpy(flat.reshape(images[l].shape)[None]).to(cuda_device)
+    assert some_hidden
+    assert np.array_equal(st.stitch_batch(poisoned)[0].cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_feather_two_pass_form_still_matches(cuda_device, monkeypatch):
+    """$MCS_TILED_BAND=0 (and plans the fused form cannot express: more than two outer layers per tile, feathers over
+    more than 32 pixels) composite with the overwrite kernel and re-evaluate the bands in a second pass."""
+    n, h, w, c = 3, 120, 200, 3
+    st, states, labels, images = synthetic_chain(n, h, w, c, kind="noise", xoffset=2, yoffset=7)
+    monkeypatch.setenv("MCS_TILED_BAND", "0")
+    st.feather_log2 = 3
+    assert np.array_equal(st.stitch(images), feather_model.feather_chain(states, labels, images, 3))
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.tiled_stats()["band_fused"] == 0 and plan.handle.last_variant() == 3
+    monkeypatch.delenv("MCS_TILED_BAND")
+    st.__dict__.pop("_engine", None)
+    st.feather_log2 = 6   # 64 pixels: beyond the six weight bits of the overlay descriptors
+    assert np.array_equal(st.stitch(images), feather_model.feather_chain(states, labels, images, 6))
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.tiled_stats()["band_fused"] == 0 and plan.handle.last_variant() == 3
 
 
 @pytest.mark.gpu
@@ -71,6 +125,7 @@ def test_feather_on_the_fly_band_kernel_and_many_frames(cuda_device, monkeypatch
     sets = [synthetic_chain(n, h, w, c, kind="noise", frame_index=f)[3] for f in range(11)]
     batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
     refs = [feather_model.feather_chain(states, labels, s, log2) for s in sets]
+    monkeypatch.setenv("MCS_TILED_BAND", "0")      # the two-pass form is what this test is about
     for table in ("1", "0"):
         monkeypatch.setenv("MCS_FEATHER_TABLE", table)
         st.__dict__.pop("_engine", None)          # new plan: the switch is read when the plan is built

@@ -72,12 +72,31 @@ def test_run_returns_with_the_panoramas_on_the_host(cuda_device):
     assert np.array_equal(out[F - 1].numpy(), ref) and np.array_equal(out[0].numpy(), ref)
 
 
-def test_feather_mode_uploads_whole_frames(cuda_device):
+def test_feather_mode_keeps_the_window_uploads_when_fused(cuda_device, monkeypatch):
+    """Fused feather form (BAND tiles): the plan knows what the band samples read, so the pipeline still
+    uploads windows only and the panoramas match the specification; the two-pass form needs whole frames."""
+    import torch
+    from oracle import feather_model
     st, states, labels, images = synthetic_chain(3, 120, 200, 3, kind="noise")
     st.feather_log2 = 2
     shapes = [images[l].shape for l in labels]
+    whole = sum(int(np.prod(s)) for s in shapes)
     pipe = SequencePipeline(st, shapes, cuda_device, chunk=2, depth=2)
-    assert pipe.bytes_per_frame()[0] == sum(int(np.prod(s)) for s in shapes)
+    assert 0 < pipe.bytes_per_frame()[0] < whole
+    F = 3
+    sets = [synthetic_chain(3, 120, 200, 3, kind="noise", frame_index=f)[3] for f in range(F)]
+    host = {l: torch.from_numpy(np.stack([s[l] for s in sets])).pin_memory() for l in labels}
+    out = torch.empty((F,) + pipe.plan.out_shape(), dtype=torch.uint8).pin_memory()
+    for slot in pipe.slots:                      # stale bytes outside the windows must never show
+        for t in slot["src"]:
+            t.fill_(0xA5)
+    pipe.run(host, out)
+    for f in range(F):
+        assert np.array_equal(out[f].numpy(), feather_model.feather_chain(states, labels, sets[f], 2))
+    monkeypatch.setenv("MCS_TILED_BAND", "0")
+    st2, _, _, _ = synthetic_chain(3, 120, 200, 3, kind="noise")
+    st2.feather_log2 = 2
+    assert SequencePipeline(st2, shapes, cuda_device, chunk=2, depth=2).bytes_per_frame()[0] == whole
 
 
 def test_single_call_numpy_path_uploads_only_the_visible_windows(cuda_device):
