@@ -192,13 +192,39 @@ int mcs_stitch_u8(const mcs_plan* plan, const uint8_t* const* src,
  * every paste over F = 2^n pixels inside the pasted rectangle: with a = min(F, 1 + distance to
  * the nearest rectangle edge), a pixel there becomes (a*inner + (F-a)*warped + F/2) >> n where
  * the warped camera has a tap inside its source.  Extension with no reference counterpart
- * (SURVEY.md section 8 row f1); specification in oracle/feather_model.py.  Not supported for
- * plans with super-mode crops.
+ * (SURVEY.md section 8 row f1); specification in oracle/feather_model.py.
+ *
+ * Up to feather_log2 = 5, and when no tile blends with more than two outer cameras, the seam
+ * bands are blended INSIDE the tiled kernel (BAND tiles: one staged box per camera involved,
+ * blend in registers, one launch; mcs_plan_source_windows / _spans then cover what the bands
+ * read).  Otherwise a second pass re-evaluates the bands and the source windows are whole frames.
+ * Equivalent to mcs_plan_set_blend(plan, feather_log2, NULL, NULL, NULL).
  */
 int mcs_plan_set_feather(mcs_plan* plan, int feather_log2);
 
+/*
+ * mcs_plan_set_blend - the blend mode with per-stage weight maps and explicit paste rectangles.
+ *   paste_xyxy   host [n_layers][4] or NULL: rectangle of layer k, in output coordinates, as the
+ *                NEXT stage pasted it (the running canvas of stage k+1, StitcherClass.py:240-241)
+ *                - what the visible rectangle of mcs_plan_create was before later super-mode
+ *                crops (:248-251) cut it.  Must contain the visible rectangle.  NULL keeps the
+ *                rectangles given to mcs_plan_create.
+ *   weight_maps  host [n_layers] pointers or NULL.  weight_maps[k], k >= 1, is the uint8 weight
+ *                of the running canvas at stage k in units of 1/F over layer k-1's pasted
+ *                rectangle ((py1-py0) rows of (px1-px0) values, map_pitch[k] bytes apart; values
+ *                above F count as F): the pixel becomes (a*canvas + (F-a)*warped + F/2) >> n
+ *                where a < F and the warped camera touches its source.  A NULL entry keeps the
+ *                distance ramp of mcs_plan_set_feather.  With feather_log2 = 0 a map of {0, 1}
+ *                is a mask: 0 lets the warped camera through, 1 is the reference's overwrite.
+ * Weight maps and cut rectangles exist only in the fused form (see above): the call fails with
+ * MCS_ERR_UNSUPPORTED (and leaves the plan in overwrite mode) when the plan cannot take it.
+ */
+int mcs_plan_set_blend(mcs_plan* plan, int feather_log2, const int32_t* paste_xyxy,
+                       const uint8_t* const* weight_maps, const int64_t* map_pitch);
+
 /* Which kernel variant the last mcs_stitch_u8 on this plan launched
- * (diagnostics for tests / bench): 0 = none yet, 1 = gather, 2 = tiled, 3 = feather. */
+ * (diagnostics for tests / bench): 0 = none yet, 1 = gather, 2 = tiled, 3 = overwrite pass +
+ * feather band pass, 4 = tiled with the seam bands blended in the same launch. */
 int mcs_plan_last_variant(const mcs_plan* plan);
 
 /* Pin the kernel variant of a plan: 0 = automatic (tiled when the plan and the buffers allow

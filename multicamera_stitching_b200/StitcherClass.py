@@ -59,6 +59,10 @@ class Stitcher(Debugger):
     # Class-level default: an object unpickled from a configuration the REFERENCE saved is built without
     # __init__ and has no blend-mode attribute.
     feather_log2 = 0
+    # Optional weight maps of the pastes (extension, include/mcs.h mcs_plan_set_blend): a list with one entry per
+    # stage, None or a uint8 array of the shape of that stage's imageB (the running canvas) holding the canvas'
+    # weight in units of 1 / 2**feather_log2; None everywhere = the distance ramp of feather_log2.
+    blend_weights = None
 
     def __init__(self, images_dic, super_mode=False):
         # labels sorted like np.sort(images_dic.keys()) (reference :61)
@@ -137,7 +141,7 @@ class Stitcher(Debugger):
             return images_dic[self.img_labels[-1]]
         frames = [images_dic[label] for label in self.img_labels]
         out = _composite(self._engine_(), self.stitchers, frames, batched=False, debugger=self,
-                         feather_log2=getattr(self, "feather_log2", 0))
+                         feather_log2=getattr(self, "feather_log2", 0), blend_weights=self.blend_weights)
         if draw_descriptors and not _is_tensor(out):
             out = self._draw_overlays(out, frames)
         return out
@@ -180,12 +184,12 @@ class Stitcher(Debugger):
         tensor ``[F, H_out, W_out, C]``.  Extension of the reference API."""
         frames = [frames_dic[label] for label in self.img_labels]
         return _composite(self._engine_(), self.stitchers, frames, batched=True, out=out, debugger=self,
-                          feather_log2=getattr(self, "feather_log2", 0))
+                          feather_log2=getattr(self, "feather_log2", 0), blend_weights=self.blend_weights)
 
     def plan(self, img_shapes, device=None):
         """Compiled plan (``engine.CompiledPlan``) for frames of these shapes."""
         return self._engine_().plan_for(self.stitchers, [tuple(s) for s in img_shapes], device,
-                                        feather_log2=getattr(self, "feather_log2", 0))
+                                        feather_log2=getattr(self, "feather_log2", 0), blend_weights=self.blend_weights)
 
     # -- persistence -----------------------------------------------------------
     def save_stitcher(self, save_path):
@@ -493,7 +497,7 @@ def _segments(stages, frame_shapes, debugger=None):
     return segs
 
 
-def _composite(engine, stages, frames, batched, out=None, debugger=None, feather_log2=0):
+def _composite(engine, stages, frames, batched, out=None, debugger=None, feather_log2=0, blend_weights=None):
     """Run the fused kernel for this chain on these frames."""
     import torch  # local: keeps `import StitcherClass` cheap for calibration-only users
 
@@ -507,9 +511,14 @@ def _composite(engine, stages, frames, batched, out=None, debugger=None, feather
     device = frames[0].device if on_device else engine.device
     n = int(frames[0].shape[0]) if batched else None
 
+    if blend_weights is not None and len(blend_weights) != len(stages):
+        raise ValueError("blend_weights must list one entry per stage (%d), got %d" % (len(stages), len(blend_weights)))
+    weight_of = {} if blend_weights is None else {id(st): w for st, w in zip(stages, blend_weights)}
+
     def plan_for(sub_stages, sub_shapes):
         try:
-            return engine.plan_for(sub_stages, sub_shapes, device, feather_log2=feather_log2)
+            return engine.plan_for(sub_stages, sub_shapes, device, feather_log2=feather_log2,
+                                   blend_weights=[weight_of.get(id(st)) for st in sub_stages] if weight_of else None)
         except PlanUnsupported as e:
             if debugger is not None:
                 debugger.debugger(DEBUG_LEVEL_0, "[STITCHER] {}".format(e), log_type="err")

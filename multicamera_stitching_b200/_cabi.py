@@ -22,7 +22,7 @@ ABI_VERSION = 1
 # every symbol include/mcs.h declares
 EXPORTS = (
     "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_create_maps", "mcs_plan_destroy",
-    "mcs_plan_owned_pixels", "mcs_plan_source_windows", "mcs_plan_source_spans", "mcs_copy_window_u8", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_last_variant",
+    "mcs_plan_owned_pixels", "mcs_plan_source_windows", "mcs_plan_source_spans", "mcs_copy_window_u8", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_set_blend", "mcs_plan_last_variant",
     "mcs_plan_force_variant", "mcs_plan_rows_need_padding", "mcs_plan_promise_padded_rows",
     "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_plan_tiled_stats", "mcs_launch_count",
     "mcs_match_hamming_top2", "mcs_match_l2_top2", "mcs_ransac_homography", "mcs_resize_linear_u8",
@@ -93,6 +93,8 @@ def load(build_if_missing=False):
     lib.mcs_plan_promise_padded_rows.argtypes = [_vp, ctypes.c_int]
     lib.mcs_plan_set_feather.restype = ctypes.c_int
     lib.mcs_plan_set_feather.argtypes = [_vp, ctypes.c_int]
+    lib.mcs_plan_set_blend.restype = ctypes.c_int
+    lib.mcs_plan_set_blend.argtypes = [_vp, ctypes.c_int, _c_i32p, ctypes.POINTER(ctypes.c_void_p), _c_i64p]
     lib.mcs_plan_tiled_ctas_per_sm.restype = ctypes.c_int
     lib.mcs_plan_tiled_ctas_per_sm.argtypes = [_vp]
     lib.mcs_plan_tiled_status.restype = ctypes.c_char_p
@@ -258,6 +260,33 @@ class Plan(object):
 
     def set_feather(self, feather_log2):
         check(_lib.mcs_plan_set_feather(self._h, int(feather_log2)), "mcs_plan_set_feather")
+
+    def set_blend(self, feather_log2, paste=None, weight_maps=None):
+        """``paste``: ``[n_layers, 4]`` int32 or None; ``weight_maps``: list of n_layers optional 2-D uint8 arrays
+        (entry k = weights of the paste of stage k over layer k-1's pasted rectangle) or None."""
+        n = self.n_layers
+        p_ptr = None
+        if paste is not None:
+            paste = np.ascontiguousarray(paste, dtype=np.int32).reshape(n, 4)
+            p_ptr = paste.ctypes.data_as(_c_i32p)
+        m_ptr, pitch_ptr, keep = None, None, []
+        if weight_maps is not None and any(m is not None for m in weight_maps):
+            if len(weight_maps) != n:
+                raise ValueError("weight_maps must list %d entries (one per layer, entry 0 unused)" % n)
+            ptrs = (ctypes.c_void_p * n)()
+            pitches = np.zeros(n, np.int64)
+            for k, m in enumerate(weight_maps):
+                if m is None:
+                    continue
+                m = np.ascontiguousarray(m, dtype=np.uint8)
+                if m.ndim != 2:
+                    raise ValueError("weight map %d must be 2-D" % k)
+                keep.append(m)
+                ptrs[k] = m.ctypes.data
+                pitches[k] = m.strides[0]
+            m_ptr, pitch_ptr = ptrs, pitches.ctypes.data_as(_c_i64p)
+            keep.append(pitches)
+        check(_lib.mcs_plan_set_blend(self._h, int(feather_log2), p_ptr, m_ptr, pitch_ptr), "mcs_plan_set_blend")
 
     def tiled_ctas_per_sm(self):
         return int(_lib.mcs_plan_tiled_ctas_per_sm(self._h))

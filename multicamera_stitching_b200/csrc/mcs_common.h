@@ -159,6 +159,7 @@ struct mcs_plan {
                              // each class, then n_tiles
     // feather mode, fused form (mcs_tiles.cu): BAND tiles are the first n_band tiles of the table
     int band_fused;          // the tiled kernel blends the seam bands itself (no second pass)
+    int blend_custom;        // weight maps or cut (super-mode) rectangles: only the fused form computes them
     int n_band;
     int band_max_ov;         // most outer layers any BAND tile blends with (sizes the kernel's overlay buffer)
     int4* d_band_issue;      // [n_band][1 + MCS_BAND_MAX_OVERLAYS] {layer, bx, by, box bytes | n_overlays << 24}

@@ -212,6 +212,8 @@ extern "C" int mcs_plan_destroy(mcs_plan* plan) {
     mcs_feather_free_table(plan);
     if (plan->d_strips) cudaFree(plan->d_strips);
     if (plan->d_strip_prefix) cudaFree(plan->d_strip_prefix);
+    for (int k = 0; k < MCS_MAX_LAYERS; ++k)
+        if (plan->d_wmap[k]) cudaFree(plan->d_wmap[k]);
     mcs_plan_free_tiles(plan);
     free_maps(plan);
     delete plan;
@@ -231,7 +233,7 @@ extern "C" int mcs_plan_source_windows(const mcs_plan* plan, int32_t* xyxy) {
     MCS_CHECK_ARG(plan != nullptr && xyxy != nullptr, "mcs_plan_source_windows: NULL argument");
     // The feather band samples outer cameras inside the pasted rectangles, i.e. outside the
     // pixels they own: there every frame counts in full.
-    const bool known = plan->src_win_valid && (plan->feather_log2 == 0 || plan->band_fused);
+    const bool known = plan->src_win_valid && ((plan->feather_log2 == 0 && !plan->blend_custom) || plan->band_fused);
     for (int k = 0; k < plan->n_layers; ++k) {
         xyxy[4 * k + 0] = known ? plan->src_win[k][0] : 0;
         xyxy[4 * k + 1] = known ? plan->src_win[k][1] : 0;
@@ -248,7 +250,7 @@ extern "C" int mcs_plan_source_spans(const mcs_plan* plan, int layer, int band_r
     const McsLayer& L = plan->layers[layer];
     const int n_bands = (L.src_h + band_rows - 1) / band_rows;
     const int* span = plan->h_row_span[layer];
-    const bool known = plan->src_win_valid && (plan->feather_log2 == 0 || plan->band_fused) && span != nullptr;
+    const bool known = plan->src_win_valid && ((plan->feather_log2 == 0 && !plan->blend_custom) || plan->band_fused) && span != nullptr;
     for (int b = 0; b < n_bands; ++b) {
         int x0 = known ? INT_MAX : 0, x1 = known ? INT_MIN : L.src_w;
         for (int r = b * band_rows; known && r < (b + 1) * band_rows && r < L.src_h; ++r) {
@@ -344,14 +346,51 @@ static void rebuild_tiles(mcs_plan* plan) {
     mcs_plan_build_tiles(plan);
 }
 
+static void free_wmaps(mcs_plan* plan) {
+    for (int k = 0; k < MCS_MAX_LAYERS; ++k) {
+        if (plan->d_wmap[k]) cudaFree(plan->d_wmap[k]);
+        plan->d_wmap[k] = nullptr;
+    }
+}
+
 extern "C" int mcs_plan_set_feather(mcs_plan* plan, int feather_log2) {
-    MCS_CHECK_ARG(plan != nullptr, "mcs_plan_set_feather: plan is NULL");
-    MCS_CHECK_ARG(feather_log2 >= 0 && feather_log2 <= 12, "mcs_plan_set_feather: feather_log2=%d outside 0..12",
+    return mcs_plan_set_blend(plan, feather_log2, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mcs_plan_set_blend(mcs_plan* plan, int feather_log2, const int32_t* paste_xyxy,
+                                  const uint8_t* const* weight_maps, const int64_t* map_pitch) {
+    MCS_CHECK_ARG(plan != nullptr, "mcs_plan_set_blend: plan is NULL");
+    MCS_CHECK_ARG(feather_log2 >= 0 && feather_log2 <= 12, "mcs_plan_set_blend: feather_log2=%d outside 0..12",
                   feather_log2);
+    bool any_map = false;
+    for (int k = 1; weight_maps && k < plan->n_layers; ++k) any_map = any_map || weight_maps[k] != nullptr;
+    MCS_CHECK_ARG(!any_map || map_pitch != nullptr, "mcs_plan_set_blend: weight maps without their pitches");
+    MCS_CHECK_ARG(!any_map || feather_log2 <= MCS_BAND_MAX_LOG2,
+                  "mcs_plan_set_blend: weight maps take feather_log2 <= %d (got %d)", MCS_BAND_MAX_LOG2, feather_log2);
     free_strips(plan);
-    const bool had = plan->feather_log2 > 0;
+    free_wmaps(plan);
+    const bool had = plan->feather_log2 > 0 || plan->blend_custom;
     plan->feather_log2 = 0;
-    if (feather_log2 == 0) {
+    plan->blend_custom = 0;
+    if (paste_xyxy) {
+        for (int k = 0; k < plan->n_layers; ++k) {
+            McsLayer& L = plan->layers[k];
+            L.px0 = paste_xyxy[4 * k]; L.py0 = paste_xyxy[4 * k + 1]; L.px1 = paste_xyxy[4 * k + 2]; L.py1 = paste_xyxy[4 * k + 3];
+            const bool empty = L.rx1 <= L.rx0 || L.ry1 <= L.ry0;
+            if (!empty && (L.px0 > L.rx0 || L.py0 > L.ry0 || L.px1 < L.rx1 || L.py1 < L.ry1)) {
+                mcs_set_error("mcs_plan_set_blend: layer %d: the pasted rectangle [%d,%d,%d,%d) does not contain the visible "
+                              "one [%d,%d,%d,%d)", k, L.px0, L.py0, L.px1, L.py1, L.rx0, L.ry0, L.rx1, L.ry1);
+                return MCS_ERR_INVALID;
+            }
+        }
+    }
+    bool cut = false;   // some rectangle was cut after it was pasted (super-mode crops): distances run to the pasted edges
+    for (int k = 0; k + 1 < plan->n_layers; ++k) {
+        const McsLayer& L = plan->layers[k];
+        if (L.rx1 > L.rx0 && L.ry1 > L.ry0)
+            cut = cut || L.px0 != L.rx0 || L.py0 != L.ry0 || L.px1 != L.rx1 || L.py1 != L.ry1;
+    }
+    if (feather_log2 == 0 && !any_map) {
         if (had) rebuild_tiles(plan);
         return MCS_OK;
     }
@@ -361,9 +400,46 @@ extern "C" int mcs_plan_set_feather(mcs_plan* plan, int feather_log2) {
         const McsLayer& i = plan->layers[k - 1];
         const bool empty_i = i.rx1 <= i.rx0 || i.ry1 <= i.ry0;
         if (!empty_i && (o.rx0 > i.rx0 || o.ry0 > i.ry0 || o.rx1 < i.rx1 || o.ry1 < i.ry1)) {
-            mcs_set_error("mcs_plan_set_feather: layer rectangles are not nested (layer %d)", k);
+            mcs_set_error("mcs_plan_set_blend: layer rectangles are not nested (layer %d)", k);
             return MCS_ERR_UNSUPPORTED;
         }
+    }
+    for (int k = 1; any_map && k < plan->n_layers; ++k) {
+        if (!weight_maps[k]) continue;
+        const McsLayer& in = plan->layers[k - 1];
+        const int mw = in.px1 - in.px0, mh = in.py1 - in.py0;
+        if (mw <= 0 || mh <= 0) continue;
+        if (map_pitch[k] < mw) {
+            mcs_set_error("mcs_plan_set_blend: weight map %d: pitch %lld < %d columns", k, (long long)map_pitch[k], mw);
+            free_wmaps(plan);
+            return MCS_ERR_INVALID;
+        }
+        cudaError_t e = cudaMalloc(&plan->d_wmap[k], (size_t)mw * mh);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2D(plan->d_wmap[k], (size_t)mw, weight_maps[k], (size_t)map_pitch[k], (size_t)mw, (size_t)mh,
+                             cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            free_wmaps(plan);
+            mcs_set_error("mcs_plan_set_blend: weight map %d: %s", k, cudaGetErrorString(e));
+            return MCS_ERR_CUDA;
+        }
+    }
+    plan->blend_custom = (any_map || cut) ? 1 : 0;
+    if (plan->blend_custom) {
+        // weight maps / cut rectangles exist only in the fused form (BAND tiles of the tiled kernel)
+        plan->feather_log2 = feather_log2;
+        rebuild_tiles(plan);
+        if (!plan->band_fused) {
+            plan->feather_log2 = 0;
+            plan->blend_custom = 0;
+            free_wmaps(plan);
+            rebuild_tiles(plan);
+            mcs_set_error("mcs_plan_set_blend: weight maps and super-mode crops need the fused band form of the tiled variant "
+                          "(feather_log2 <= %d, at most %d outer layers per tile, tiled variant available)",
+                          MCS_BAND_MAX_LOG2, MCS_BAND_MAX_OVERLAYS);
+            return MCS_ERR_UNSUPPORTED;
+        }
+        return MCS_OK;
     }
     // Band strips: inside the rectangle pasted at stage k (that of layer k-1), the pixels closer
     // than F - 1 to its border: top and bottom strips over the full width, left and right strips
@@ -400,7 +476,7 @@ extern "C" int mcs_plan_set_feather(mcs_plan* plan, int feather_log2) {
             e = cudaMemcpy(plan->d_strip_prefix, prefix, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
             free_strips(plan);
-            mcs_set_error("mcs_plan_set_feather: %s", cudaGetErrorString(e));
+            mcs_set_error("mcs_plan_set_blend: %s", cudaGetErrorString(e));
             return MCS_ERR_CUDA;
         }
         plan->n_strips = n;

@@ -412,9 +412,14 @@ extern "C" int mcs_stitch_u8(const mcs_plan* plan_c, const uint8_t* const* src,
         MCS_CHECK_CUDA(launch_gather<false>(plan, a, nullptr, stream));
         plan->last_variant = 1;
     }
-    if (plan->feather_log2 > 0 && plan->band_fused && plan->last_variant == 2) {
+    if (plan->band_fused && plan->last_variant == 2) {
         plan->last_variant = 4;   // the tiled kernel blended the seam bands itself (BAND tiles)
         return MCS_OK;
+    }
+    if (plan->blend_custom) {
+        mcs_set_error("mcs_stitch_u8: weight maps / super-mode feathering exist only in the tiled variant, which cannot "
+                      "serve this call: %s", blocker ? blocker : "the gather variant was forced");
+        return MCS_ERR_UNSUPPORTED;
     }
     if (plan->feather_log2 > 0 && plan->n_strips > 0) {
         // feather blend: the pass above composited with the reference's overwrite; now the seam bands

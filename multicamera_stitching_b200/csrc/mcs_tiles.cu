@@ -477,7 +477,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
     bool fused = false;
     {
         const char* env = getenv("MCS_TILED_BAND");   // "0": keep the two-pass band path (tests, experiments)
-        const bool want = plan->feather_log2 > 0 && plan->feather_log2 <= MCS_BAND_MAX_LOG2 && plan->n_layers > 1 &&
+        const bool want = (plan->feather_log2 > 0 || plan->blend_custom) && plan->feather_log2 <= MCS_BAND_MAX_LOG2 && plan->n_layers > 1 &&
                           !(env && atoi(env) == 0);
         if (want) {
             const size_t n_jobs = (size_t)n_tiles * plan->n_layers;

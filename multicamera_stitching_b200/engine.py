@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .plan import PlanUnsupported, flatten_chain, plan_maps, plan_tables, stage_signature
+from .plan import plan_paste, PlanUnsupported, flatten_chain, plan_maps, plan_tables, stage_signature
 
 
 def _stage_field(st, name):
@@ -25,7 +25,7 @@ def _round_up(v, m):
 class CompiledPlan(object):
     """A flattened chain plus its ``mcs_plan`` on one device."""
 
-    def __init__(self, flat, device, feather_log2=0):
+    def __init__(self, flat, device, feather_log2=0, blend_weights=None):
         self.flat = flat
         self.device = torch.device(device)
         self.feather_log2 = int(feather_log2)
@@ -33,8 +33,16 @@ class CompiledPlan(object):
             kind, src_hw, fwd, origin, rect = plan_tables(flat)
             self.handle = _cabi.Plan(kind, src_hw, fwd, origin, rect, flat.out_w, flat.out_h, flat.channels,
                                      maps=plan_maps(flat))
-            if self.feather_log2:
-                self.handle.set_feather(self.feather_log2)
+            maps = None
+            if blend_weights is not None and any(w is not None for w in blend_weights):
+                # stage s pastes over camera s + 1's warp: its map belongs to the layer of that camera
+                maps = [None] * len(flat.layers)
+                for k, l in enumerate(flat.layers):
+                    if l.cam >= 1 and l.cam - 1 < len(blend_weights):
+                        maps[k] = blend_weights[l.cam - 1]
+            if self.feather_log2 or maps is not None:
+                # the paste rectangles matter only when a super-mode crop cut a visible one
+                self.handle.set_blend(self.feather_log2, plan_paste(flat), maps)
             # rows that are not a multiple of 4 bytes: run() always passes them through its
             # zero-padded scratch buffers, which is what the tiled kernel needs to serve them
             self.pad_rows = self.handle.tiled_status() == "" and self.handle.rows_need_padding()
@@ -191,7 +199,7 @@ class CompositeEngine(object):
             self._device = torch.device("cuda", torch.cuda.current_device())
         return torch.device(self._device)
 
-    def plan_for(self, stages, cam_shapes, device=None, feather_log2=0):
+    def plan_for(self, stages, cam_shapes, device=None, feather_log2=0, blend_weights=None):
         """Compiled plan for this chain state and these frame shapes, or None
         when no stage is calibrated (decided on the host, no device needed)."""
         shapes = tuple(tuple(int(v) for v in s) for s in cam_shapes)
@@ -200,17 +208,18 @@ class CompositeEngine(object):
             return None
         device = torch.device(device) if device is not None else self.device
         feather_log2 = int(feather_log2 or 0)
-        key = (str(device), shapes, sig, feather_log2)
+        wkey = None
+        if blend_weights is not None and any(w is not None for w in blend_weights):
+            wkey = tuple(None if w is None else (np.asarray(w).shape, hash(np.ascontiguousarray(w, dtype=np.uint8).tobytes()))
+                         for w in blend_weights)
+        key = (str(device), shapes, sig, feather_log2, wkey)
         if key in self._plans:
             self._plans[key] = self._plans.pop(key)      # most recently used last
         else:
             flat = flatten_chain(stages, shapes)
-            if feather_log2 and any(_stage_field(st, "super_mode") and _stage_field(st, "cachedAH") is not None
-                                    for st in stages):
-                raise PlanUnsupported("the feather blend does not support super_mode crops")
             while len(self._plans) >= self.max_plans:     # evict the least recently used, one at a time
                 self._plans.pop(next(iter(self._plans)))
-            self._plans[key] = CompiledPlan(flat, device, feather_log2) if flat is not None else None
+            self._plans[key] = CompiledPlan(flat, device, feather_log2, blend_weights) if flat is not None else None
         return self._plans[key]
 
     def upload(self, cam, arr, device, bands=None):

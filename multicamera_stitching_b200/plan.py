@@ -19,7 +19,9 @@ LAYER_WARP = 1
 LAYER_REMAP = 2   # coordinates from a fixed-point map pair (prewarp.py), not from a homography
 
 # ``map``: for LAYER_REMAP the (int16 H x W x 2, uint16 H x W) pair cv2.convertMaps produces
-Layer = namedtuple("Layer", "cam kind H ox oy rect src_hw map", defaults=(None,))
+# ``paste``: the layer's rectangle as the next stage pasted it (never cut by later super-mode crops,
+# only shifted with them) - what the feather blend measures its distances against; None = ``rect``
+Layer = namedtuple("Layer", "cam kind H ox oy rect src_hw map paste", defaults=(None, None))
 FlatPlan = namedtuple("FlatPlan", "layers out_w out_h channels ndim")
 
 
@@ -101,9 +103,12 @@ def flatten_chain(stages, cam_shapes):
         if (y1 - y0, x1 - x0) != (hB, wB):
             raise ValueError("could not broadcast input array from shape %r into shape %r"
                              % ((hB, wB) + tail, (y1 - y0, x1 - x0) + tail))
-        layers = [l._replace(ox=l.ox + x0, oy=l.oy + y0,
-                             rect=(l.rect[0] + x0, l.rect[1] + y0, l.rect[2] + x0, l.rect[3] + y0))
+        def shifted(r, dx, dy):
+            return None if r is None else (r[0] + dx, r[1] + dy, r[2] + dx, r[3] + dy)
+        layers = [l._replace(ox=l.ox + x0, oy=l.oy + y0, rect=shifted(l.rect, x0, y0), paste=shifted(l.paste, x0, y0))
                   for l in layers]
+        # the outermost layer so far is the canvas this stage pastes: remember the rectangle it is pasted as
+        layers[-1] = layers[-1]._replace(paste=layers[-1].rect)
         layers.append(Layer(s + 1, LAYER_WARP, np.array(H, dtype=np.float64).reshape(3, 3), 0, 0,
                             (0, 0, W, Hh), (shapeA[0], shapeA[1])))
         cw, ch = W, Hh
@@ -117,7 +122,9 @@ def flatten_chain(stages, cam_shapes):
                 r = (max(0, l.rect[0] - cx0), max(0, l.rect[1] - cy0),
                      min(cw, l.rect[2] - cx0), min(ch, l.rect[3] - cy0))
                 r = (r[0], r[1], max(r[0], r[2]), max(r[1], r[3]))
-                clipped.append(l._replace(ox=l.ox - cx0, oy=l.oy - cy0, rect=r))
+                clipped.append(l._replace(ox=l.ox - cx0, oy=l.oy - cy0, rect=r,
+                                          paste=None if l.paste is None else
+                                          (l.paste[0] - cx0, l.paste[1] - cy0, l.paste[2] - cx0, l.paste[3] - cy0)))
             layers = clipped
         cur_shape = (ch, cw) + tail
 
@@ -137,6 +144,12 @@ def plan_tables(flat):
     for i, l in enumerate(flat.layers):
         fwd[i] = np.eye(3).ravel() if l.H is None else np.asarray(l.H, dtype=np.float64).ravel()
     return kind, src_hw, fwd, origin, rect
+
+
+def plan_paste(flat):
+    """``[n, 4]`` int32 paste rectangles for ``mcs_plan_set_blend`` (a layer that was never pasted - the last
+    one - and layers whose rectangle was not cut report their visible rectangle)."""
+    return np.array([l.rect if l.paste is None else l.paste for l in flat.layers], dtype=np.int32).reshape(-1, 4)
 
 
 def plan_maps(flat):

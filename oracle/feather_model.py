@@ -19,7 +19,13 @@ Definition, per stage (same walk as ``stitcher_ref.stitch_pair``):
   ``touched`` and a < F, and imageB elsewhere; outside the rectangle it is
   ``warped``.  Every stage rounds to uint8 like the reference's chain does.
 
-The super-mode crop (:248-251) is not supported in this mode.
+Weight maps generalise the ramp: ``weights[k]`` (one optional ``hB x wB`` integer array per
+stage, values 0 .. F, larger values count as F) replaces ``a`` of stage k; the ramp is the
+instance ``a = min(F, 1 + distance)``.  A map that is F everywhere is the reference's overwrite;
+with ``feather_log2 == 0`` a {0, 1} map is a mask (0 shows the warped camera where it touches its
+source).  The super-mode crop (:248-251) is applied after the blended paste, exactly where
+``stitcher_ref.stitch_pair`` applies it after the overwrite: distances and maps refer to the
+pasted rectangle, whatever later crops cut away.
 """
 import numpy as np
 import cv2
@@ -40,21 +46,31 @@ def touched_mask(M, src_hw, dsize):
     return okx & oky
 
 
-def feather_pair(st, images, feather_log2):
+def ramp_weights(shape_hw, feather_log2):
+    """The distance ramp as a weight map: ``min(F, 1 + distance to the nearest edge)``."""
+    hB, wB = shape_hw
+    F = 1 << feather_log2
+    yy, xx = np.mgrid[0:hB, 0:wB]
+    a = np.minimum(np.minimum(xx, wB - 1 - xx), np.minimum(yy, hB - 1 - yy)) + 1
+    return np.minimum(a, F).astype(np.int32)
+
+
+def feather_pair(st, images, feather_log2, weights=None):
     imageB, imageA = images
     if st["cachedAH"] is None:
         return imageB
-    if st["super_mode"]:
-        raise ValueError("feather blend does not support super_mode")
     F = 1 << feather_log2
     W, H = int(st["ABSize"][0]), int(st["ABSize"][1])
     bx, by = int(st["Bpts"][0][0]), int(st["Bpts"][0][1])
     hB, wB = imageB.shape[:2]
     warped = cv2.warpPerspective(src=imageA, M=st["cachedAH"], dsize=(W, H))
     touched = touched_mask(st["cachedAH"], imageA.shape[:2], (W, H))
-    yy, xx = np.mgrid[0:hB, 0:wB]
-    a = np.minimum(np.minimum(xx, wB - 1 - xx), np.minimum(yy, hB - 1 - yy)) + 1
-    a = np.minimum(a, F).astype(np.int32)
+    if weights is None:
+        a = ramp_weights((hB, wB), feather_log2)
+    else:
+        a = np.minimum(np.asarray(weights).astype(np.int32), F)
+        if a.shape != (hB, wB):
+            raise ValueError("weight map of shape %r for a %d x %d paste" % (a.shape, hB, wB))
     outer = warped[by:by + hB, bx:bx + wB].astype(np.int32)
     inner = imageB.astype(np.int32)
     t = touched[by:by + hB, bx:bx + wB] & (a < F)
@@ -65,13 +81,16 @@ def feather_pair(st, images, feather_log2):
     blend = (a3 * inner + (F - a3) * outer + (F >> 1)) >> feather_log2
     dst = warped.copy()
     dst[by:by + hB, bx:bx + wB] = np.where(t3, blend, inner).astype(np.uint8)
+    if st["super_mode"]:   # StitcherClass.py:248-251
+        dst = dst[st["y_limits"][0]:st["y_limits"][1], st["x_limits"][0]:st["x_limits"][1]]
     return dst
 
 
-def feather_chain(states, img_labels, images_dic, feather_log2):
-    """The chain of ``stitcher_ref.stitch_chain`` with the feathered paste."""
+def feather_chain(states, img_labels, images_dic, feather_log2, weights=None):
+    """The chain of ``stitcher_ref.stitch_chain`` with the blended paste; ``weights`` = one optional
+    map per stage."""
     dst = None
     for i in range(len(img_labels) - 1):
         pair = (images_dic[img_labels[0]] if i == 0 else dst, images_dic[img_labels[i + 1]])
-        dst = feather_pair(states[i], pair, feather_log2)
+        dst = feather_pair(states[i], pair, feather_log2, None if weights is None else weights[i])
     return dst if dst is not None else images_dic[img_labels[-1]]
