@@ -46,7 +46,7 @@ WORKLOADS = {
     "cfg1_3x720p": (3, 720, 1280, 64, 64),
     "cfg2_6x1080p": (6, 1080, 1920, 64, 32),
     "cfg3_8x2160p": (8, 2160, 3840, 16, 8),
-    "ns_8x1080p": (8, 1080, 1920, 48, 24),     # the geometry north_star's 70 % target names
+    "ns_8x1080p": (8, 1080, 1920, 48, 32),     # the geometry north_star's 70 % target names
 }
 DEFAULT_WORKLOAD = "ns_8x1080p"
 LAUNCHES_PER_STEP = 5
@@ -424,6 +424,79 @@ def extra_sequence(device, rank, world, ctx, frames, chunk):
             "collectives_on_data_path": 0}
 
 
+def extra_blend(device, rank, world, ctx, peak, feather=3, chunk=16):
+    """BASELINE config 2's "feather blend" on its own geometry (6 x 1080p): every paste softened over 2**feather
+    pixels, the seam bands blended inside the tiled kernel (BAND tiles, one launch).  Device-resident rate and
+    parity against the blend specification (oracle/feather_model.py; ours - the reference only overwrites), and
+    the end-to-end rate through the sequence pipeline, which keeps its window uploads in this mode."""
+    import torch
+    from multicamera_stitching_b200.sequence import SequencePipeline, pinned_like
+    w = Resident("cfg2_6x1080p", device, rank, feather=feather)
+    parity, _, _ = w.parity(feather) if rank == 0 else (None, None, None)
+    ms, n_launch = time_resident(w, ctx, 4, 3, 3)
+    pps = world * w.batch * 4 * 3 / (ms * 1e-3)
+    stats = w.plan.handle.tiled_stats()
+    variant = w.plan.handle.last_variant()
+    pipe = SequencePipeline(w.st, w.shapes, device, chunk=chunk, depth=3)
+    R = 32
+    host = {l: pinned_like((R,) + tuple(w.images[l].shape)) for l in w.labels}
+    for l in w.labels:
+        for f in range(R):
+            host[l][f].copy_(torch.from_numpy(w.ring[f % w.distinct][l]))
+    out = pinned_like((R,) + w.plan.out_shape())
+    pipe.run(host, out)
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pipe.run(host, out, 0, 8 * R, ring=True)
+    e1.record()
+    ctx.barrier()
+    e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    h2d, d2h = pipe.bytes_per_frame()
+    whole = sum(int(np.prod(sh)) for sh in w.shapes)
+    del pipe, host, out
+    w.free()
+    torch.cuda.empty_cache()
+    return {"workload": "cfg2 geometry, feather blend over %d px (reference: overwrite only)" % (1 << feather),
+            "value": pps, "unit": "panoramas/s", "launch_ms": ms / max(n_launch, 1), "kernel_variant": variant,
+            "band_tiles": stats.get("band"), "band_fused": stats.get("band_fused"), "tiles": stats.get("tiles"),
+            "parity_vs_blend_specification": parity,
+            "e2e_panoramas_per_s": world * 8 * R / (e2e_ms * 1e-3), "h2d_bytes_per_panorama": h2d,
+            "whole_frame_bytes_per_panorama": whole, "d2h_bytes_per_panorama": d2h}
+
+
+def extra_recorded(device, n_sets=48, quality=90):
+    """A recorded capture in the reference's own format (data.csv + JPEG files, data_capture_node.py:107-130) on
+    config 2's geometry, composited through ``recorded.stitch_capture``: JPEG decode on the host thread pool one
+    batch ahead of the pipeline (video_mapping_node.py:105-130 replays while it stitches).  Rank 0 only."""
+    import shutil
+    import torch
+    from multicamera_stitching_b200 import recorded, synthetic
+    st, homographies, labels, images = build_chain("cfg2_6x1080p")
+    tmp = tempfile.mkdtemp(prefix="mcs_capture_")
+    try:
+        distinct = [synthetic.make_frames(6, 1080, 1920, 3, frame_index=f, kind="smooth") for f in range(4)]
+        recorded.write_capture(tmp, [distinct[f % 4] for f in range(n_sets)], quality=quality)
+        seq = recorded.RecordedSequence(tmp)
+        runner = recorded.CaptureRunner(st, seq, device=device, batch=16)     # pipeline + pinned buffers, once
+        out = torch.empty((n_sets,) + runner.out_shape(), dtype=torch.uint8, pin_memory=True)
+        runner.run(0, 32, out[:32])                                           # warm-up (plan, page cache)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        panos = runner.run(0, n_sets, out)
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        runner._decode(0, 0, 16)            # the JPEG decode alone, into the runner's pinned buffers
+        decode = 16 / (time.perf_counter() - t1)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"workload": "recorded capture: %d frame-sets of 6 x 1080p JPEG (quality %d), data.csv format of the reference"
+                        % (n_sets, quality),
+            "value": n_sets / dt, "unit": "panoramas/s", "api": "recorded.CaptureRunner.run (decode-ahead, SequencePipeline; buffers allocated once)",
+            "decode_only_frame_sets_per_s": decode, "decode_threads": min(16, os.cpu_count() or 1),
+            "panoramas": int(panos.shape[0])}
+
+
 # ---------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -542,8 +615,10 @@ def run_ours(args, rank, local_rank, world):
             if name != args.workload:
                 extra[name] = extra_resident(name, device, rank, ctx, world, peak)
         extra["cfg5_sequence"] = extra_sequence(device, rank, world, ctx, args.sequence_frames, args.chunk)
+        extra["cfg2_feather_blend"] = extra_blend(device, rank, world, ctx, peak, chunk=args.chunk)
         if rank == 0:
             extra["cfg4_recalibration"] = extra_recalibration(device)
+            extra["recorded_capture"] = extra_recorded(device)
         barrier()
 
     ctx.close()

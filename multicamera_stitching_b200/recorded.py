@@ -157,45 +157,69 @@ def write_capture(path, frame_sets, capture_id=0, timestamps=None, quality=80, i
     return stamps
 
 
+class CaptureRunner(object):
+    """Composites frame ranges of one capture: a ``SequencePipeline`` plus two sets of pinned decode buffers,
+    allocated once (pinned allocations cost far more than compositing a short range) and reused by every
+    :meth:`run`.  While the pipeline composites batch k from one buffer set, a helper thread decodes batch k + 1
+    into the other (the reference's player replays the next frames while the current ones are being stitched,
+    video_mapping_node.py:105-130)."""
+
+    def __init__(self, stitcher, seq, capture=0, device=None, chunk=16, depth=3, batch=32, workers=None):
+        import torch
+        from .sequence import SequencePipeline
+        self.stitcher, self.seq, self.capture = stitcher, seq, capture
+        self.batch, self.workers = int(batch), workers
+        self.labels = [str(l) for l in stitcher.img_labels]
+        if sorted(self.labels) != sorted(seq.labels()):
+            raise ValueError("stitcher cameras %r differ from the recording's %r" % (self.labels, seq.labels()))
+        first = seq.load_frame_set(capture, 0)
+        shapes = [first[l].shape for l in self.labels]
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.pipe = SequencePipeline(stitcher, shapes, self.device, chunk=chunk, depth=depth)
+        self.sets = [None, None]
+
+    def out_shape(self):
+        return self.pipe.plan.out_shape()
+
+    def _decode(self, i, s, e):
+        """Decode frame-sets ``[s, e)`` into buffer set ``i & 1`` (allocated at the full batch size on first use)."""
+        from .sequence import pinned_like
+        cur = self.sets[i & 1]
+        if cur is None:
+            first = self.seq.load_frame_set(self.capture, s)
+            cur = self.sets[i & 1] = {l: pinned_like((self.batch,) + tuple(first[l].shape)) for l in self.seq.labels()}
+        view = {l: t[:e - s] for l, t in cur.items()}
+        self.seq.read_batch(self.capture, s, e, out=view, workers=self.workers)
+        return view
+
+    def run(self, lo, hi, out=None):
+        """Composite frame-sets ``[lo, hi)``; returns the pinned host tensor ``[hi - lo, H_out, W_out, C]``
+        (``out`` when given)."""
+        from .sequence import pinned_like
+        if out is None:
+            out = pinned_like((hi - lo,) + self.out_shape())
+        ranges = [(s, min(hi, s + self.batch)) for s in range(lo, hi, self.batch)]
+        with ThreadPoolExecutor(max_workers=1) as ahead:
+            pending = ahead.submit(self._decode, 0, *ranges[0]) if ranges else None
+            for i, (s, e) in enumerate(ranges):
+                bufs = pending.result()
+                if i + 1 < len(ranges):
+                    # the other buffer set: batch i - 1 has left it (SequencePipeline.run blocks until its downloads landed)
+                    pending = ahead.submit(self._decode, i + 1, *ranges[i + 1])
+                self.pipe.run({l: bufs[l] for l in self.stitcher.img_labels}, out[s - lo:e - lo])
+        return out
+
+
 def stitch_capture(stitcher, seq, capture=0, lo=0, hi=None, device=None, chunk=16, depth=3, batch=32,
                    rank=0, world_size=1, workers=None):
     """Composite frame-sets ``[lo, hi)`` of a capture (this rank's share of them) and return
-    ``(first_frame, panoramas)`` with ``panoramas`` a host uint8 tensor ``[n, H_out, W_out, C]``."""
-    import torch
-    from .sequence import SequencePipeline, pinned_like, shard_range
+    ``(first_frame, panoramas)`` with ``panoramas`` a host uint8 tensor ``[n, H_out, W_out, C]``.
+    One-shot form of :class:`CaptureRunner` (which keeps its pipeline and pinned buffers between calls)."""
+    from .sequence import shard_range
     hi = seq.n_frames(capture) if hi is None else hi
     a, b = shard_range(hi - lo, world_size, rank)
     a, b = lo + a, lo + b
     if b <= a:
         return a, None
-    labels = [str(l) for l in stitcher.img_labels]
-    if sorted(labels) != sorted(seq.labels()):
-        raise ValueError("stitcher cameras %r differ from the recording's %r" % (labels, seq.labels()))
-    first = seq.load_frame_set(capture, a)
-    shapes = [first[l].shape for l in labels]
-    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    pipe = SequencePipeline(stitcher, shapes, device, chunk=chunk, depth=depth)
-    out = pinned_like((b - a,) + pipe.plan.out_shape())
-    # Decode-ahead (the reference's player replays the next frames while the current ones are being
-    # stitched, video_mapping_node.py:105-130): two sets of pinned decode buffers; while the pipeline
-    # composites batch k from one set, a helper thread decodes batch k + 1 into the other.
-    ranges = [(s, min(b, s + batch)) for s in range(a, b, batch)]
-    sets = [None, None]
-
-    def decode(i):
-        s, e = ranges[i]
-        cur = sets[i & 1]
-        if cur is None or int(next(iter(cur.values())).shape[0]) != e - s:
-            sets[i & 1] = seq.read_batch(capture, s, e, workers=workers)
-        else:
-            seq.read_batch(capture, s, e, out=cur, workers=workers)
-        return sets[i & 1]
-
-    with ThreadPoolExecutor(max_workers=1) as ahead:
-        pending = ahead.submit(decode, 0)
-        for i, (s, e) in enumerate(ranges):
-            bufs = pending.result()
-            if i + 1 < len(ranges):
-                pending = ahead.submit(decode, i + 1)   # the other buffer set: batch i - 1 has left it (run() blocks)
-            pipe.run({l: bufs[l] for l in stitcher.img_labels}, out[s - a:e - a])
-    return a, out
+    runner = CaptureRunner(stitcher, seq, capture, device, chunk, depth, batch, workers)
+    return a, runner.run(a, b)

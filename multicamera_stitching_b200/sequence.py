@@ -26,15 +26,24 @@ def shard_range(n_frames, world_size, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def ring_chunks(lo, hi, ring, chunk):
+def ring_chunks(lo, hi, ring, chunk, ramp=False):
     """How frames ``[lo, hi)`` of a sequence held in a ring of ``ring`` host slots (frame ``f`` in slot
     ``f % ring``) are cut into pipeline chunks: ``(slot, n)`` pairs of at most ``chunk`` consecutive
-    slots that never wrap around the end of the ring."""
+    slots that never wrap around the end of the ring.
+
+    ``ramp=True``: the chunks grow 1, 2, 4, ... up to ``chunk`` at the start and halve towards the end.
+    Nothing overlaps the upload of the first chunk or the download of the last one, so with full-size
+    chunks a run of ``F`` frames pays about ``2 * chunk / F`` of its transfer time for filling and
+    draining the pipeline (13 % for 240 frame-sets in chunks of 16); ramped, about ``2 / F``."""
     out = []
     f = int(lo)
+    cap = 1 if ramp else int(chunk)
     while f < hi:
         r0 = f % ring
-        n = min(int(chunk), hi - f, ring - r0)
+        n = min(int(chunk), cap, hi - f, ring - r0)
+        if ramp:
+            n = min(n, max(1, (hi - f + 1) // 2))
+            cap = min(int(chunk), cap * 2)
         out.append((r0, n))
         f += n
     return out
@@ -113,10 +122,9 @@ class SequencePipeline(object):
             start = torch.cuda.current_stream()
             for s in (self.s_in, self.s_k, self.s_out):
                 s.wait_stream(start)
-            i = 0
-            for f0 in range(lo, hi, self.chunk):
-                self._chunk(i, host_frames, host_out, f0, min(self.chunk, hi - f0))
-                i += 1
+            # one "ring" as long as the sequence: the same ramped schedule, no wrap-around
+            for i, (f0, n) in enumerate(ring_chunks(lo, hi, max(F, hi), self.chunk, ramp=True)):
+                self._chunk(i, host_frames, host_out, f0, n)
             self._finish(start, sync)
         return hi - lo
 
@@ -167,7 +175,7 @@ class SequencePipeline(object):
             start = torch.cuda.current_stream()
             for s in (self.s_in, self.s_k, self.s_out):
                 s.wait_stream(start)
-            for i, (r0, n) in enumerate(ring_chunks(lo, hi, R, self.chunk)):
+            for i, (r0, n) in enumerate(ring_chunks(lo, hi, R, self.chunk, ramp=True)):
                 self._chunk(i, host_frames, host_out, r0, n)
             self._finish(start, sync)
         return hi - lo

@@ -100,12 +100,17 @@ def test_ring_chunks_cover_the_range_without_wrapping():
     """Config 5 cycles a long sequence through a ring of host slots: the chunks of any frame range
     cover it exactly once, in order, and never run past the end of the ring."""
     for lo, hi, ring, chunk in ((0, 100, 32, 16), (3, 14, 5, 2), (1250, 2500, 32, 16), (7, 8, 4, 16), (0, 0, 8, 4)):
-        chunks = ring_chunks(lo, hi, ring, chunk)
-        assert sum(n for _, n in chunks) == hi - lo
-        f = lo
-        for slot, n in chunks:
-            assert slot == f % ring and 1 <= n <= chunk and slot + n <= ring
-            f += n
+        for ramp in (False, True):
+            chunks = ring_chunks(lo, hi, ring, chunk, ramp=ramp)
+            assert sum(n for _, n in chunks) == hi - lo
+            f = lo
+            for slot, n in chunks:
+                assert slot == f % ring and 1 <= n <= chunk and slot + n <= ring
+                f += n
+    # ramped: the pipeline fills and drains on single frame-sets, full-size chunks in between
+    sizes = [n for _, n in ring_chunks(0, 240, 240, 16, ramp=True)]
+    assert sizes[:5] == [1, 2, 4, 8, 16] and sizes[-1] == 1 and max(sizes) == 16 and sizes.count(16) >= 10
+    assert [n for _, n in ring_chunks(0, 3, 8, 16, ramp=True)] == [1, 1, 1]
     # the shards of a 10 000-frame sequence over 8 ranks tile it, and so do their chunks
     total = 0
     for rank in range(8):
