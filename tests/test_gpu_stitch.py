@@ -361,3 +361,77 @@ def test_realigned_sources_with_odd_frame_strides(cuda_device):
     assert plan.handle.last_variant() == 2
     for f in range(3):
         _check(out[f].cpu().numpy(), stitcher_ref.stitch_chain(states, labels, sets[f]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,h,w", [(8, 1080, 1920), (8, 2160, 3840)])
+def test_full_size_ownership_partition(cuda_device, n, h, w):
+    """Size-independent property at BASELINE.json's full sizes (the default bench geometry and config 3), no oracle
+    involved: with camera k painted in the constant colour (c_k, 255 - c_k, 128), bilinear resampling of a constant
+    is that constant wherever all four taps lie inside the source, and a border pixel (taps mixed with the zero
+    fill) scales all three channels by the same weight, so it matches no camera's colour.  The panorama is then
+    made of background zeros, camera colours and a thin ring of border mixes, and the count of every colour is
+    what ``mcs_plan_owned_pixels`` - the figure behind the roofline's algorithmic bytes - reports, up to that ring."""
+    import torch
+    st, states, labels, images = synthetic_chain(n, h, w, 3)
+    colours = [(16 + 24 * k, 255 - (16 + 24 * k), 128) for k in range(n)]
+    frames = {}
+    for k, l in enumerate(labels):
+        f = torch.empty((1, h, w, 3), dtype=torch.uint8, device=cuda_device)
+        for c in range(3):
+            f[..., c] = colours[k][c]
+        frames[l] = f
+    pano = st.stitch_batch(frames)[0].to(torch.int32)
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.last_variant() == 2
+    owned = plan.owned_pixels()
+    layer_of_cam = {l.cam: i for i, l in enumerate(plan.flat.layers)}
+    key = pano[..., 0] * 65536 + pano[..., 1] * 256 + pano[..., 2]
+    accounted = int((key == 0).sum())
+    ring_total = 0
+    for k in range(n):
+        ck = colours[k][0] * 65536 + colours[k][1] * 256 + colours[k][2]
+        exact = int((key == ck).sum())
+        own = owned[layer_of_cam[k]]
+        ring = 2 * (h + w) * 3          # owned pixels whose taps straddle the source border
+        assert own - ring <= exact <= own, (k, exact, own)
+        ring_total += own - exact
+        accounted += exact
+    # what is neither background nor a camera colour is a border mix of an owned pixel
+    assert int(key.numel()) - accounted <= ring_total
+    assert int((key == 0).sum()) >= int(key.numel()) - sum(owned)
+
+
+@pytest.mark.gpu
+def test_full_size_blend_reduces_to_the_overwrite(cuda_device):
+    """Size-independent property of the blend modes at config 2's full size: weight maps that are F everywhere
+    are the reference's overwrite (StitcherClass.py:240-241), bit for bit, through the BAND-aware kernel."""
+    import torch
+    st, states, labels, images = synthetic_chain(6, 1080, 1920, 3)
+    frames = {l: torch.from_numpy(images[l][None]).to(cuda_device) for l in labels}
+    hard = st.stitch_batch(frames).clone()
+    shapes = []
+    shapeB = images[labels[0]].shape
+    for sb in st.stitchers:
+        shapes.append(tuple(shapeB[:2]))
+        shapeB = sb.result_shape()
+    st.feather_log2 = 4
+    st.blend_weights = [np.full(sh, 16, np.uint8) for sh in shapes]
+    assert torch.equal(st.stitch_batch(frames), hard)
+    # a real ramp on one stage only changes pixels within F - 1 of that stage's pasted rectangle border
+    st.blend_weights = None
+    soft = st.stitch_batch(frames)
+    changed = (soft != hard).any(dim=-1)[0]
+    assert bool(changed.any())
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.last_variant() == 4
+    # the seam band of stage k lies within F - 1 = 15 pixels inside the border of layer k - 1's rectangle
+    inner_ok = torch.zeros_like(changed)
+    for l in plan.flat.layers[:-1]:
+        x0, y0, x1, y1 = l.rect
+        band = torch.zeros_like(changed)
+        band[y0:y1, x0:x1] = True
+        if y1 - y0 > 30 and x1 - x0 > 30:
+            band[y0 + 15:y1 - 15, x0 + 15:x1 - 15] = False
+        inner_ok |= band
+    assert not bool((changed & ~inner_ok).any())
