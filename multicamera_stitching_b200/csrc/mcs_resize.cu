@@ -105,30 +105,41 @@ mcs_resize_linear_kernel(const __grid_constant__ ResizeArgs a) {
 #define RSEP_TW 128
 #define RSEP_TH 16
 #define RSEP_SMEM_MAX (40 * 1024)
+#define RSEP_TILES_Y 4   // tiles a CTA walks down its column strip
 
 template <int C>
 __global__ void __launch_bounds__(256)
 mcs_resize_sep_kernel(const __grid_constant__ ResizeArgs a) {
     extern __shared__ __align__(16) uint16_t hbuf[];   // [rows][RSEP_TW * C]
-    const int x0 = blockIdx.x * RSEP_TW, y0 = blockIdx.y * RSEP_TH;
+    __shared__ int4 rowc[RSEP_TH];   // per tile row {first source row, second (relative to ry0), b0 << 16, b1 << 16}
+    const int x0 = blockIdx.x * RSEP_TW;
     const int tid = threadIdx.x;
     const uint8_t* src = a.src + (long long)blockIdx.z * a.src_frame_stride;
-    const int y_last = min(y0 + RSEP_TH, a.dst_h) - 1;
-    int ry0, ry1;
-    {
-        int s0, s1, w0, w1;
-        linear_coef(y0, a.scale_y, a.src_h, false, s0, w0, w1);
-        linear_coef(y_last, a.scale_y, a.src_h, false, s1, w0, w1);
-        ry0 = max(0, min(a.src_h - 1, s0));
-        ry1 = max(0, min(a.src_h - 1, s1 + 1));
-    }
     constexpr int ROW = RSEP_TW * C;   // uint16 per staged row
-    {   // phase 1
-        const int col = tid & (RSEP_TW - 1);
-        const int x = min(x0 + col, a.dst_w - 1);
-        int sx, a0, a1;
-        linear_coef(x, a.scale_x, a.src_w, true, sx, a0, a1);
-        const int o0 = sx * C, o1 = min(sx + 1, a.src_w - 1) * C;
+    // column coefficients: once per CTA, which walks RSEP_TILES_Y tiles down its 128-column strip (the float64
+    // coefficient recipe and the address set-up cost ~300 instructions per thread, as much as 8 pixels of work)
+    const int col = tid & (RSEP_TW - 1);
+    int sx, a0, a1;
+    linear_coef(min(x0 + col, a.dst_w - 1), a.scale_x, a.src_w, true, sx, a0, a1);
+    const int o0 = sx * C, o1 = min(sx + 1, a.src_w - 1) * C;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int x_first = x0 + 4 * lane;
+    const int n_px = min(4, a.dst_w - x_first);   // <= 0: this thread has no output columns
+
+    for (int ty = 0; ty < RSEP_TILES_Y; ++ty) {
+        const int y0 = (blockIdx.y * RSEP_TILES_Y + ty) * RSEP_TH;
+        if (y0 >= a.dst_h) break;                  // uniform over the CTA
+        const int y_last = min(y0 + RSEP_TH, a.dst_h) - 1;
+        int ry0, ry1;
+        {
+            int s0, s1, w0, w1;
+            linear_coef(y0, a.scale_y, a.src_h, false, s0, w0, w1);
+            linear_coef(y_last, a.scale_y, a.src_h, false, s1, w0, w1);
+            ry0 = max(0, min(a.src_h - 1, s0));
+            ry1 = max(0, min(a.src_h - 1, s1 + 1));
+        }
+        if (ty) __syncthreads();                   // the previous tile's vertical pass is done with hbuf / rowc
+        // phase 1: horizontal pass, h >> 4 of every source row the tile needs
         for (int r = ry0 + (tid >> 7); r <= ry1; r += 2) {
             const uint8_t* row = src + (long long)r * a.src_pitch;
             uint16_t* h = hbuf + (r - ry0) * ROW + col * C;
@@ -136,44 +147,42 @@ mcs_resize_sep_kernel(const __grid_constant__ ResizeArgs a) {
             for (int c = 0; c < C; ++c)
                 h[c] = (uint16_t)((__ldg(row + o0 + c) * a0 + __ldg(row + o1 + c) * a1) >> 4);
         }
-    }
-    __syncthreads();
-    // phase 2
-    const int lane = tid & 31, warp = tid >> 5;
-    const int x_first = x0 + 4 * lane;
-    if (x_first >= a.dst_w) return;
-    const int n_px = min(4, a.dst_w - x_first);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int y = y0 + warp + 8 * half;
-        if (y >= a.dst_h) break;
-        int sy, b0, b1;
-        linear_coef(y, a.scale_y, a.src_h, false, sy, b0, b1);
-        const int r0 = max(0, min(a.src_h - 1, sy)) - ry0, r1 = max(0, min(a.src_h - 1, sy + 1)) - ry0;
-        // 4 pixels x C values = 4 * C uint16 = C 8-byte words per source row
-        const uint2* h0 = reinterpret_cast<const uint2*>(hbuf + r0 * ROW + 4 * lane * C);
-        const uint2* h1 = reinterpret_cast<const uint2*>(hbuf + r1 * ROW + 4 * lane * C);
-        uint8_t px[4 * C];
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-            const uint2 u = h0[k], v = h1[k];
-            const uint32_t uu[2] = {u.x, u.y}, vv[2] = {v.x, v.y};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int p0 = (uu[j >> 1] >> (16 * (j & 1))) & 0xffff, p1 = (vv[j >> 1] >> (16 * (j & 1))) & 0xffff;
-                px[4 * k + j] = (uint8_t)((((b0 * p0) >> 16) + ((b1 * p1) >> 16) + 2) >> 2);
-            }
+        if (tid < RSEP_TH) {
+            int sy, b0, b1;
+            linear_coef(min(y0 + tid, a.dst_h - 1), a.scale_y, a.src_h, false, sy, b0, b1);
+            rowc[tid] = make_int4(max(0, min(a.src_h - 1, sy)) - ry0, max(0, min(a.src_h - 1, sy + 1)) - ry0, b0 << 16, b1 << 16);
         }
-        uint8_t* out = a.dst + (long long)blockIdx.z * a.dst_frame_stride + (long long)y * a.dst_pitch +
-                       (long long)x_first * C;
-        if (n_px == 4 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
-            uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+        __syncthreads();
+        // phase 2: (((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2 with (b * h) >> 16 = umulhi(b << 16, h): two
+        // IMAD.HI.U32 chained through their addend and one shift per value (b <= 2048, h <= 32640: no overflow)
+        if (n_px <= 0) continue;
 #pragma unroll
-            for (int wd = 0; wd < C; ++wd)
-                o32[wd] = (uint32_t)px[4 * wd] | ((uint32_t)px[4 * wd + 1] << 8) | ((uint32_t)px[4 * wd + 2] << 16) |
-                          ((uint32_t)px[4 * wd + 3] << 24);
-        } else {
-            for (int b = 0; b < n_px * C; ++b) out[b] = px[b];
+        for (int half = 0; half < 2; ++half) {
+            const int y = y0 + warp + 8 * half;
+            if (y >= a.dst_h) break;
+            const int4 rc = rowc[warp + 8 * half];
+            const uint32_t b0 = (uint32_t)rc.z, b1 = (uint32_t)rc.w;
+            // 4 pixels x C values = 4 * C uint16 = C 8-byte words per source row
+            const uint2* h0 = reinterpret_cast<const uint2*>(hbuf + rc.x * ROW + 4 * lane * C);
+            const uint2* h1 = reinterpret_cast<const uint2*>(hbuf + rc.y * ROW + 4 * lane * C);
+            uint32_t o32[C];   // the 4 * C output bytes in memory order
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const uint2 u = h0[k], v = h1[k];
+                const uint32_t v0 = (__umulhi(b0, u.x & 0xffffu) + __umulhi(b1, v.x & 0xffffu) + 2u) >> 2;
+                const uint32_t v1 = (__umulhi(b0, u.x >> 16) + __umulhi(b1, v.x >> 16) + 2u) >> 2;
+                const uint32_t v2 = (__umulhi(b0, u.y & 0xffffu) + __umulhi(b1, v.y & 0xffffu) + 2u) >> 2;
+                const uint32_t v3 = (__umulhi(b0, u.y >> 16) + __umulhi(b1, v.y >> 16) + 2u) >> 2;
+                o32[k] = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+            }
+            uint8_t* out = a.dst + (long long)blockIdx.z * a.dst_frame_stride + (long long)y * a.dst_pitch +
+                           (long long)x_first * C;
+            if (n_px == 4 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+#pragma unroll
+                for (int wd = 0; wd < C; ++wd) reinterpret_cast<uint32_t*>(out)[wd] = o32[wd];
+            } else {
+                for (int b = 0; b < n_px * C; ++b) out[b] = (uint8_t)(o32[b >> 2] >> (8 * (b & 3)));
+            }
         }
     }
 }
@@ -212,7 +221,7 @@ extern "C" int mcs_resize_linear_u8(const uint8_t* src, int src_w, int src_h, in
     const long long sep_rows = (long long)(RSEP_TH * a.scale_y) + 4;
     const long long sep_smem = sep_rows * RSEP_TW * channels * 2;
     if (!a.area2 && sep_smem <= RSEP_SMEM_MAX) {
-        const dim3 sgrid((dst_w + RSEP_TW - 1) / RSEP_TW, (dst_h + RSEP_TH - 1) / RSEP_TH, n_frames);
+        const dim3 sgrid((dst_w + RSEP_TW - 1) / RSEP_TW, (dst_h + RSEP_TH * RSEP_TILES_Y - 1) / (RSEP_TH * RSEP_TILES_Y), n_frames);
         switch (channels) {
             case 1: mcs_resize_sep_kernel<1><<<sgrid, 256, (size_t)sep_smem, stream>>>(a); break;
             case 3: mcs_resize_sep_kernel<3><<<sgrid, 256, (size_t)sep_smem, stream>>>(a); break;

@@ -1,5 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_sequence.py tests/test_gpu_stitch.py tests/test_stitcher_api.py tests/test_gpu_fuzz.py tests/test_feather.py -m gpu -x -q 2>&1 | tail -5
-python scripts/bench_single_call.py
-MCS_HOST_THREADS=4 python scripts/bench_single_call.py
-MCS_HOST_THREADS=16 python scripts/bench_single_call.py
-MCS_HOST_THREADS=1 python scripts/bench_single_call.py
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:mcs_resize_sep -s 18 -c 1 -o gpurun_out/prof_r2_resize python scripts/bench_prewarp.py > gpurun_out/ncu_resize.log 2>&1
+tail -2 gpurun_out/ncu_resize.log | cut -c1-200
