@@ -466,6 +466,7 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
     // the plan keeps the two-pass band path of mcs_stitch.cu)
     struct BandInfo {
         int n;
+        int zero_base;   // the owner contributes nothing (untouched): no box of it is staged
         int layer[MCS_BAND_MAX_OVERLAYS], bx[MCS_BAND_MAX_OVERLAYS], by[MCS_BAND_MAX_OVERLAYS];
         TileBounds b[MCS_BAND_MAX_OVERLAYS];
     };
@@ -541,14 +542,22 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
             if (t.cls == MCS_TILE_COPY) {
                 b.min_sx = t.cx0 + t.c0 - L.ox; b.max_sx = t.cx0 + t.c1 - 1 - L.ox;
                 b.min_sy = t.y0 - L.oy;         b.max_sy = t.y0 + t.h - 1 - L.oy;
+                b.touched = 1;
             }
             t.cls = MCS_TILE_BAND;
-            t.bx = 4 * floor_div(b.min_sx * C, 16);
-            t.by = b.min_sy;
-            need_w = ((b.max_sx + 2) * C + 3) / 4 - t.bx + 1;
-            need_h = b.max_sy + 2 - b.min_sy;
-            grow(t.layer, std::max(0, b.min_sx), std::max(0, b.min_sy), std::min(L.src_w, b.max_sx + 2),
-                 std::min(L.src_h, b.max_sy + 2));
+            if (b.touched) {
+                t.bx = 4 * floor_div(b.min_sx * C, 16);
+                t.by = b.min_sy;
+                need_w = ((b.max_sx + 2) * C + 3) / 4 - t.bx + 1;
+                need_h = b.max_sy + 2 - b.min_sy;
+                grow(t.layer, std::max(0, b.min_sx), std::max(0, b.min_sy), std::min(L.src_w, b.max_sx + 2),
+                     std::min(L.src_h, b.max_sy + 2));
+            } else {
+                // the owner's warp touches nothing here (background inside its rectangle): the value so far is 0,
+                // the kernel stages no box of the owner and starts from zeros
+                binfo[i].zero_base = 1;
+                t.bx = t.by = 0;
+            }
             for (int o = 0; o < binfo[i].n; ++o) {
                 const int k = binfo[i].layer[o];
                 const McsLayer& K = plan->layers[k];
@@ -684,7 +693,8 @@ void mcs_plan_build_tiles(mcs_plan* plan) {
         t.reserved = t.layer >= 0 ? bw4[t.layer] * 4 * bh[t.layer] : 0;
         if (i < n_band) {
             tile_passes[i] = (uint8_t)bi.n;
-            t.reserved |= bi.n << 24;   // the tile record and the issue record carry the number of overlays
+            t.reserved |= (bi.n << 24) | (bi.zero_base << 28);   // the tile record and the issue record carry the number of overlays
+                                                                 // and the zero-base flag
             int4* r = &band_issue[(size_t)i * (1 + MCS_BAND_MAX_OVERLAYS)];
             r[0] = make_int4(t.layer, t.bx, t.by, t.reserved);
             for (int o = 0; o < MCS_BAND_MAX_OVERLAYS; ++o)
