@@ -12,6 +12,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A persistent kernel that waits for a box nobody issues would hang the whole run: every GPU test gets a
+    time limit (pytest-timeout, thread method: the process is ended, the run reports the test)."""
+    try:
+        import pytest_timeout  # noqa: F401
+    except ImportError:
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(180, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def cuda_device():
     import torch

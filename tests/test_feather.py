@@ -257,3 +257,24 @@ def test_feather_ramp_in_super_mode(cuda_device, n, h, w, c, log2):
     st2, states2, labels2, images2 = synthetic_chain(n, h, w, c, kind="noise", super_mode=True)
     st2.feather_log2 = log2
     assert np.array_equal(st2.stitch(images2), feather_model.feather_chain(states2, labels2, images2, log2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spread", ["0", "1"])
+def test_fused_bands_over_several_frame_blocks(cuda_device, monkeypatch, spread):
+    """BAND chunks of frame block b + 1 follow the COPY / ZERO chunks of block b in the sweep, and with
+    $MCS_TILED_BAND_SPREAD they are spread between the ordinary resampled chunks: either way the box issuer
+    enters a BAND chunk only when the consumers get there.  11 frames in blocks of 4."""
+    import torch
+    monkeypatch.setenv("MCS_TILED_FRAME_BLOCK", "4")
+    monkeypatch.setenv("MCS_TILED_BAND_SPREAD", spread)
+    n, h, w, c, log2 = 5, 270, 480, 3, 3
+    st, states, labels, images = synthetic_chain(n, h, w, c, kind="noise", xoffset=2, yoffset=7)
+    st.feather_log2 = log2
+    sets = [synthetic_chain(n, h, w, c, kind="noise", frame_index=f)[3] for f in range(11)]
+    batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
+    out = st.stitch_batch(batch).cpu().numpy()
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.last_variant() == 4
+    for f in range(11):
+        assert np.array_equal(out[f], feather_model.feather_chain(states, labels, sets[f], log2)), f

@@ -435,3 +435,20 @@ def test_full_size_blend_reduces_to_the_overwrite(cuda_device):
             band[y0 + 15:y1 - 15, x0 + 15:x1 - 15] = False
         inner_ok |= band
     assert not bool((changed & ~inner_ok).any())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_frames", [65, 67, 130])
+def test_frame_counts_whose_last_block_is_shorter_than_the_split(cuda_device, n_frames):
+    """64-frame blocks with 1-3 frames left over: the launcher must not cut the last tiles of such a block into
+    chunks without frames (tests/test_issuer_protocol.py: the box issuer would starve).  Every frame against the
+    single-frame result."""
+    import torch
+    st, states, labels, images = synthetic_chain(4, 120, 200, 3, kind="noise")
+    ref = stitcher_ref.stitch_chain(states, labels, images)
+    batch = {l: torch.from_numpy(images[l]).to(cuda_device)[None].expand(n_frames, -1, -1, -1).contiguous() for l in labels}
+    out = st.stitch_batch(batch)
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    assert plan.handle.last_variant() == 2
+    want = torch.from_numpy(ref).to(cuda_device)
+    assert bool((out == want[None]).all())
