@@ -96,3 +96,41 @@ def test_plan_and_stitch_errors_on_the_device(cuda_device):
         with pytest.raises(_cabi.McsError, match="feather_log2"):
             plan.set_feather(13)
         torch.cuda.synchronize()
+
+
+def test_set_blend_rejects_a_null_plan_before_touching_the_device():
+    lib = _cabi.load()
+    assert lib.mcs_plan_set_blend(None, 1, None, None, None) == MCS_ERR_INVALID and "plan is NULL" in _last()
+
+
+@pytest.mark.gpu
+def test_set_blend_errors_leave_the_plan_in_a_usable_mode(cuda_device):
+    """mcs_plan_set_blend: bad arguments are refused with a message; a blend the plan cannot take in its fused
+    form (weight maps with feather_log2 > 5) is MCS_ERR_UNSUPPORTED and the plan keeps the reference's overwrite."""
+    import torch
+    from helpers import synthetic_chain
+    from oracle import stitcher_ref
+    st, states, labels, images = synthetic_chain(3, 120, 200, 3, kind="noise")
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    h = plan.handle
+    n = h.n_layers
+    lib = _cabi.load()
+    assert lib.mcs_plan_set_blend(h._h, 13, None, None, None) == MCS_ERR_INVALID and "feather_log2" in _last()
+    # weight maps without pitches
+    m = np.full((120, 200), 4, np.uint8)
+    ptrs = (ctypes.c_void_p * n)()
+    ptrs[1] = m.ctypes.data
+    assert lib.mcs_plan_set_blend(h._h, 3, None, ptrs, None) == MCS_ERR_INVALID and "pitches" in _last()
+    # maps beyond the six weight bits of the overlay descriptors
+    with pytest.raises(_cabi.McsError):
+        h.set_blend(6, None, [None, m] + [None] * (n - 2))
+    # a paste rectangle that does not contain the visible one
+    paste = np.array([l.rect for l in plan.flat.layers], np.int32)
+    paste[0, 2] -= 10
+    with pytest.raises(_cabi.McsError):
+        h.set_blend(2, paste, None)
+    # after every refusal: the overwrite, bit for bit
+    h.set_blend(0)
+    dev = {l: torch.from_numpy(images[l][None]).to(cuda_device) for l in labels}
+    assert np.array_equal(st.stitch_batch(dev)[0].cpu().numpy(), stitcher_ref.stitch_chain(states, labels, images))
+    assert h.last_variant() == 2
