@@ -4,8 +4,8 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A *step* is one pass of the hot path over one batch of synthetic frame-sets.  Default workload: 8 x 1080p
-cameras into one panorama - the geometry north_star's 70 % target is quoted on - with 5 launches of 48
-frame-sets per step (20 steps time 100 launches; inputs 2.4 GB + outputs 1.5 GB per launch, far beyond the
+cameras into one panorama - the geometry north_star's 70 % target is quoted on - with 5 launches of 64
+frame-sets per step (20 steps time 100 launches; inputs 3.2 GB + outputs 2.1 GB per launch, far beyond the
 126 MB L2, so no launch sees a warm cache).  BASELINE.json's other configurations ride along as ``extra``
 records of the same line: config 2 (6 x 1080p) and config 3 (8 x 2160p) device-resident with their roofline
 fractions, config 4 (recalibration of four 1080p pairs through the batched matchKeypoints, host refit
@@ -46,7 +46,7 @@ WORKLOADS = {
     "cfg1_3x720p": (3, 720, 1280, 64, 64),
     "cfg2_6x1080p": (6, 1080, 1920, 64, 32),
     "cfg3_8x2160p": (8, 2160, 3840, 16, 8),
-    "ns_8x1080p": (8, 1080, 1920, 48, 32),     # the geometry north_star's 70 % target names
+    "ns_8x1080p": (8, 1080, 1920, 64, 32),     # the geometry north_star's 70 % target names
 }
 DEFAULT_WORKLOAD = "ns_8x1080p"
 LAUNCHES_PER_STEP = 5
