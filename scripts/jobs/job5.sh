@@ -1,1 +1,1 @@
-timeout 500 python -m pytest tests/test_gpu_fuzz.py -m gpu -x -q -k blend 2>&1 | tail -15
+for n in 1 2 4; do PROBE_UP_STREAMS=$n timeout 200 python scripts/probe_wc_upload.py 2>&1 | grep '"pinned"' | grep windows; done

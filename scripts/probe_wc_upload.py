@@ -38,6 +38,8 @@ def main():
     d_out = torch.empty(F * 33480000 // 1, dtype=torch.uint8, device=dev)
     h_out = torch.empty(d_out.numel(), dtype=torch.uint8, pin_memory=True)
     s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    n_up = int(os.environ.get("PROBE_UP_STREAMS", "1"))     # upload streams the cameras are dealt over
+    ups = [s_up] + [torch.cuda.Stream() for _ in range(n_up - 1)]
     for kind, flags in (("pinned", 0), ("write-combined", 4)):
         h_src, keep = host_alloc(n_cam * F * fs, flags)
         h_src.fill_(7) if flags == 0 else h_src[::4096].fill_(7)
@@ -46,15 +48,18 @@ def main():
                 def up():
                     for c in range(n_cam):
                         base = h_src.data_ptr() + c * F * fs
+                        st = ups[c % n_up].cuda_stream
                         if mode == "whole":
-                            _cabi.copy_window_u8(d_src[c].data_ptr(), ROW, fs, base, ROW, fs, 0, ROW, 0, H, F, s_up.cuda_stream)
+                            _cabi.copy_window_u8(d_src[c].data_ptr(), ROW, fs, base, ROW, fs, 0, ROW, 0, H, F, st)
                         else:
                             for y0 in range(0, H, 64):
                                 _cabi.copy_window_u8(d_src[c].data_ptr(), ROW, fs, base, ROW, fs, win_b0, win_n, y0,
-                                                     min(64, H - y0), F, s_up.cuda_stream)
+                                                     min(64, H - y0), F, st)
                 reps = 6
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 torch.cuda.synchronize()
+                for u in ups[1:]:
+                    u.wait_stream(s_up)
                 e[0].record(s_up)
                 e[2].record(s_dn)
                 for _ in range(reps):
@@ -62,11 +67,13 @@ def main():
                     if duplex:
                         with torch.cuda.stream(s_dn):
                             h_out.copy_(d_out, non_blocking=True)
+                for u in ups[1:]:
+                    s_up.wait_stream(u)
                 e[1].record(s_up)
                 e[3].record(s_dn)
                 torch.cuda.synchronize()
                 up_bytes = reps * n_cam * F * H * (ROW if mode == "whole" else win_n)
-                line = {"host_memory": kind, "upload": mode, "duplex": duplex,
+                line = {"host_memory": kind, "upload": mode, "duplex": duplex, "upload_streams": n_up,
                         "h2d_gbs": up_bytes / e[0].elapsed_time(e[1]) / 1e6}
                 if duplex:
                     line["d2h_gbs"] = reps * d_out.numel() / e[2].elapsed_time(e[3]) / 1e6
