@@ -1,2 +1,2 @@
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
