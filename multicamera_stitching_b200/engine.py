@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .plan import plan_paste, PlanUnsupported, flatten_chain, plan_maps, plan_tables, stage_signature
+from .plan import flatten_chain, plan_maps, plan_paste, plan_tables, stage_signature
 
 
 def _stage_field(st, name):

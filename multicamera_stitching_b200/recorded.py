@@ -16,7 +16,6 @@ import csv
 import os
 from concurrent.futures import ThreadPoolExecutor
 
-import numpy as np
 
 HEADER = ["capture_id", "timestamp", "camera_label", "image_file"]
 
