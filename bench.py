@@ -45,7 +45,7 @@ WORKLOADS = {
     # name: (n_cams, H, W, frame-sets per launch, e2e frame-sets per step)
     "cfg1_3x720p": (3, 720, 1280, 64, 64),
     "cfg2_6x1080p": (6, 1080, 1920, 64, 32),
-    "cfg3_8x2160p": (8, 2160, 3840, 16, 8),
+    "cfg3_8x2160p": (8, 2160, 3840, 64, 8),
     "ns_8x1080p": (8, 1080, 1920, 64, 32),     # the geometry north_star's 70 % target names
 }
 DEFAULT_WORKLOAD = "ns_8x1080p"
