@@ -1,11 +1,16 @@
-t0=$(date +%s)
-timeout 900 python bench.py > gpurun_out/r2_bench_default_n1.json 2> gpurun_out/r2_bench_default_n1.err
-echo "bench wall seconds: $(( $(date +%s) - t0 ))"
-tail -2 gpurun_out/r2_bench_default_n1.err
-python - <<'PY'
-import json
-d = json.loads(open('gpurun_out/r2_bench_default_n1.json').read().strip().splitlines()[-1])
-print({k: d[k] for k in ('value','n_gpus','ms_per_step','gpu_launches')}, d['roofline']['frac'], d['roofline']['traffic'], d['clocks'])
-print(d['e2e']['value'], d['e2e']['frac_of_host_ceiling'])
-for k, v in d['extra'].items(): print(' ', k, round(v.get('value')), v.get('roofline_frac'))
-PY
+for o in 1 2 4 0; do
+MCS_TILED_ORDER=$o timeout 200 python bench.py --steps 6 --warmup 3 --no-cpu --no-e2e --workload cfg3_8x2160p --launches-per-step 2 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('cfg3 order $o', 'ms/step %.4f' % d['ms_per_step'], 'frac %.4f' % d['roofline']['frac'], d['parity'])
+"
+done
+for o in 2 4; do
+MCS_TILED_ORDER=$o timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('8x1080p order $o', 'ms/step %.4f' % d['ms_per_step'], 'frac %.4f' % d['roofline']['frac'], d['parity'])
+"
+done
