@@ -278,3 +278,39 @@ def test_fused_bands_over_several_frame_blocks(cuda_device, monkeypatch, spread)
     assert plan.handle.last_variant() == 4
     for f in range(11):
         assert np.array_equal(out[f], feather_model.feather_chain(states, labels, sets[f], log2)), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [0.62, 0.45])
+def test_fused_bands_with_large_source_boxes(cuda_device, scale):
+    """Minifying cameras: the staged source boxes grow (24 KB, 39 KB) until only three fit the ring - at the smaller
+    scale with one CTA per SM - so a BAND unit's two boxes per frame leave the issuer a look-ahead of one box.
+    Against the specification, single frames and a batch."""
+    import torch
+    from multicamera_stitching_b200 import Stitcher, synthetic
+    n, h, w, c, log2 = 3, 360, 640, 3, 3
+    images = synthetic.make_frames(n, h, w, c, 0, "noise")
+    st = Stitcher(images)
+    labels = list(st.img_labels)
+    states = []
+    shapeB = images[labels[0]].shape
+    for k in range(n - 1):
+        H = np.array([[scale, 0.02, shapeB[1] - 0.4 * w * scale], [-0.012, scale, 9.0 * (1 if k % 2 == 0 else -1)],
+                      [1e-5, -0.5e-5, 1.0]])
+        st.stitchers[k].set_homography(H, shapeA=images[labels[k + 1]].shape, shapeB=shapeB, xoffset=0, yoffset=0)
+        ost = stitcher_ref.new_state(sid=str(k))
+        stitcher_ref.geometry_from_homography(ost, H, images[labels[k + 1]].shape, shapeB, 0, 0)
+        states.append(ost)
+        shapeB = st.stitchers[k].result_shape()
+    st.feather_log2 = log2
+    ref = feather_model.feather_chain(states, labels, images, log2)
+    got = st.stitch(images)
+    assert np.array_equal(got, ref)
+    sets = [synthetic.make_frames(n, h, w, c, f, "noise") for f in range(5)]
+    batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
+    out = st.stitch_batch(batch).cpu().numpy()
+    for f in range(5):
+        assert np.array_equal(out[f], feather_model.feather_chain(states, labels, sets[f], log2)), f
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    stats = plan.handle.tiled_stats()
+    assert plan.handle.last_variant() in (3, 4) and (stats["band_fused"] == 1) == (plan.handle.last_variant() == 4)
