@@ -1,18 +1,23 @@
-timeout 300 python -m pytest tests/test_feather.py -m gpu -x -q -k "large_source" 2>&1 | tail -12
-python - <<'PY'
+cat > /tmp/san.py <<'PY'
 import sys
-sys.path.insert(0,'tests')
+sys.path.insert(0, 'tests')
 import numpy as np, torch
-from multicamera_stitching_b200 import Stitcher, synthetic
-for scale in (0.62, 0.45):
-    n,h,w,c=3,360,640,3
-    images = synthetic.make_frames(n,h,w,c,0,"noise")
-    st = Stitcher(images); labels=list(st.img_labels); shapeB=images[labels[0]].shape
-    for k in range(n-1):
-        H=np.array([[scale,0.02,shapeB[1]-0.4*w*scale],[-0.012,scale,9.0*(1 if k%2==0 else -1)],[1e-5,-0.5e-5,1.0]])
-        st.stitchers[k].set_homography(H, shapeA=images[labels[k+1]].shape, shapeB=shapeB, xoffset=0, yoffset=0); shapeB=st.stitchers[k].result_shape()
-    st.feather_log2=3
-    st.stitch(images)
-    plan=st.plan([images[l].shape for l in labels], torch.device('cuda',0))
-    print(scale, plan.handle.tiled_stats(), plan.handle.last_variant(), plan.handle.tiled_ctas_per_sm(), repr(plan.handle.tiled_status()))
+from helpers import synthetic_chain
+from oracle import feather_model, stitcher_ref
+dev = torch.device('cuda', 0)
+# overwrite, feather ramp (fused), weight maps, super mode - small geometry, a few frames
+st, states, labels, images = synthetic_chain(3, 120, 200, 3, kind="noise", xoffset=2, yoffset=7)
+assert np.array_equal(st.stitch(images), stitcher_ref.stitch_chain(states, labels, images))
+st.feather_log2 = 3
+assert np.array_equal(st.stitch(images), feather_model.feather_chain(states, labels, images, 3))
+sets = [synthetic_chain(3, 120, 200, 3, kind="noise", frame_index=f)[3] for f in range(5)]
+batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(dev) for l in labels}
+out = st.stitch_batch(batch).cpu().numpy()
+for f in range(5):
+    assert np.array_equal(out[f], feather_model.feather_chain(states, labels, sets[f], 3))
+print("sanitizer workload ok", st.plan([images[l].shape for l in labels], dev).handle.tiled_stats())
 PY
+timeout 500 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san.py 2>&1 | tail -6
+echo "memcheck rc=$?"
+timeout 500 compute-sanitizer --tool racecheck --error-exitcode 7 python /tmp/san.py 2>&1 | tail -6
+echo "racecheck rc=$?"
