@@ -1,23 +1,6 @@
-cat > /tmp/san.py <<'PY'
-import sys
-sys.path.insert(0, 'tests')
-import numpy as np, torch
-from helpers import synthetic_chain
-from oracle import feather_model, stitcher_ref
-dev = torch.device('cuda', 0)
-# overwrite, feather ramp (fused), weight maps, super mode - small geometry, a few frames
-st, states, labels, images = synthetic_chain(3, 120, 200, 3, kind="noise", xoffset=2, yoffset=7)
-assert np.array_equal(st.stitch(images), stitcher_ref.stitch_chain(states, labels, images))
-st.feather_log2 = 3
-assert np.array_equal(st.stitch(images), feather_model.feather_chain(states, labels, images, 3))
-sets = [synthetic_chain(3, 120, 200, 3, kind="noise", frame_index=f)[3] for f in range(5)]
-batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(dev) for l in labels}
-out = st.stitch_batch(batch).cpu().numpy()
-for f in range(5):
-    assert np.array_equal(out[f], feather_model.feather_chain(states, labels, sets[f], 3))
-print("sanitizer workload ok", st.plan([images[l].shape for l in labels], dev).handle.tiled_stats())
-PY
-timeout 500 compute-sanitizer --tool memcheck --error-exitcode 7 python /tmp/san.py 2>&1 | tail -6
-echo "memcheck rc=$?"
-timeout 500 compute-sanitizer --tool racecheck --error-exitcode 7 python /tmp/san.py 2>&1 | tail -6
-echo "racecheck rc=$?"
+for band in 64 1080; do for chunk in 16 32; do
+MCS_UPLOAD_BAND=$band timeout 200 python bench.py --no-extra --no-cpu --steps 20 --warmup 5 --chunk $chunk 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); e = d['e2e']
+print('band $band chunk $chunk e2e %.0f h2d MB/step %.0f frac %.3f ceil %.0f' % (e['value'], e['h2d_bytes_per_step']/1e6, e['frac_of_host_ceiling'], e['host_ceiling_panoramas_per_s']))"
+done; done
