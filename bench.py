@@ -497,6 +497,37 @@ def extra_recorded(device, n_sets=48, quality=90):
             "panoramas": int(panos.shape[0])}
 
 
+def extra_single_call(device, calls=20):
+    """The reference's own call shape, one frame-set per call: ``Stitcher.stitch(images_dic)`` with numpy frames in
+    (pageable host memory) and a numpy panorama of its own out (StitcherClass.py:114-136), on config 2, next to the
+    cv2 chain on all host threads with the same frames.  Rank 0 only; wall clock, every call blocking."""
+    import cv2
+    import torch
+    from oracle import stitcher_ref
+    st, homographies, labels, images = build_chain("cfg2_6x1080p")
+    states = oracle_states(homographies, labels, images)
+    with torch.cuda.device(device):
+        got = st.stitch(images)
+        ref = stitcher_ref.stitch_chain(states, labels, images)
+        st.stitch(images)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            st.stitch(images)
+        ms = (time.perf_counter() - t0) / calls * 1e3
+    cv2.setNumThreads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    for _ in range(4):
+        stitcher_ref.stitch_chain(states, labels, images)
+    ms_cv2 = (time.perf_counter() - t0) / 4 * 1e3
+    return {"workload": "cfg2_6x1080p, one frame-set per call", "api": "Stitcher.stitch(images_dic): numpy frames in, numpy panorama out",
+            "ms_per_call": ms, "value": 1e3 / ms, "unit": "panoramas/s", "bit_exact_vs_cv2": bool(np.array_equal(got, ref)),
+            "cv2_chain_ms_per_call": ms_cv2, "cv2_threads": os.cpu_count() or 1,
+            "h2d_bytes_per_call": int(sum(w["nbytes"] * w["rows"] for b in st._engine_().plan_for(
+                st.stitchers, [images[l].shape for l in labels], device).upload_bands().values() for w in b[2])),
+            "d2h_bytes_per_call": int(got.nbytes)}
+
+
 # ---------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -620,6 +651,7 @@ def run_ours(args, rank, local_rank, world):
         if rank == 0:
             extra["cfg4_recalibration"] = extra_recalibration(device)
             extra["recorded_capture"] = extra_recorded(device)
+            extra["single_call"] = extra_single_call(device)
         barrier()
 
     ctx.close()

@@ -164,6 +164,23 @@ int mcs_copy_window_u8(void* dst, int64_t dst_pitch_bytes, int64_t dst_frame_str
                        int64_t width_bytes, int y0, int rows, int n_frames, void* cuda_stream);
 
 /*
+ * mcs_upload_pageable_u8 - upload byte windows of PAGEABLE host frames (the numpy frames a caller of
+ * the reference's Stitcher.stitch(images_dic) holds, StitcherClass.py:114-136) through pinned staging
+ * frames the caller provides.  Window i = {x_byte0, y0, width_bytes, rows} (host int64 xywh[4 * i ..])
+ * of frame src[i] (row pitch src_pitch_bytes[i]; rows contiguous) goes to the same position of the
+ * device frame dst[i]; staging[i] is a pinned host frame of the device frame's geometry (row pitch
+ * pitch_bytes[i]).  A persistent pool of `threads` host threads copies the windows into the staging
+ * frames in pieces of about piece_bytes (<= 0: 1 MiB) and the calling thread issues the
+ * host-to-device copy of every piece on cuda_stream as soon as it has landed - instead of the
+ * driver staging one pageable cudaMemcpy after the other on the calling thread.  Returns when the
+ * last piece has been issued: the copies may still be in flight, and the staging frames must not
+ * be rewritten before cuda_stream has passed them.  Several windows may share their buffers.
+ */
+int mcs_upload_pageable_u8(int n_windows, void* const* dst, const void* const* src, void* const* staging,
+                           const int64_t* pitch_bytes, const int64_t* src_pitch_bytes, const int64_t* xywh,
+                           int64_t piece_bytes, int threads, void* cuda_stream);
+
+/*
  * mcs_stitch_u8 - composite n_frames panoramas.
  *
  * Replaces, per frame, the whole Stitcher.stitch chain (StitcherClass.py:

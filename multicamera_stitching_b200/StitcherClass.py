@@ -532,8 +532,9 @@ def _composite(engine, stages, frames, batched, out=None, debugger=None, feather
                 return plan.run(frames, out=out, n_frames=n)
             dev = [None] * len(frames)
             bands = plan.upload_bands()   # feather mode without the fused band form reports whole frames
-            for l in plan.flat.layers:   # only what the panorama can see of each camera crosses PCIe
-                dev[l.cam] = engine.upload(l.cam, frames[l.cam], device, bands[l.cam])
+            # only what the panorama can see of each camera crosses PCIe
+            for cam, t in engine.upload_frames([l.cam for l in plan.flat.layers], frames, device, bands).items():
+                dev[cam] = t
             res = plan.run(dev)
         else:
             res = None
@@ -554,9 +555,7 @@ def _composite(engine, stages, frames, batched, out=None, debugger=None, feather
                     res = plan.run(sub, out=out if i == len(segs) - 1 else None, n_frames=n)
             if on_device:
                 return res
-        host = torch.empty(res.shape, dtype=torch.uint8)
-        host.copy_(res)  # synchronous D2H into a fresh array, like cv2 allocating its result
-    return host.numpy()
+        return engine.download(res)   # blocking D2H into an array of its own, like cv2 allocating its result
 
 
 class _CompatUnpickler(pickle.Unpickler):

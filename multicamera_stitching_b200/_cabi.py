@@ -22,7 +22,7 @@ ABI_VERSION = 1
 # every symbol include/mcs.h declares
 EXPORTS = (
     "mcs_abi_version", "mcs_last_error", "mcs_plan_create", "mcs_plan_create_maps", "mcs_plan_destroy",
-    "mcs_plan_owned_pixels", "mcs_plan_source_windows", "mcs_plan_source_spans", "mcs_copy_window_u8", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_set_blend", "mcs_plan_last_variant",
+    "mcs_plan_owned_pixels", "mcs_plan_source_windows", "mcs_plan_source_spans", "mcs_copy_window_u8", "mcs_upload_pageable_u8", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_set_blend", "mcs_plan_last_variant",
     "mcs_plan_force_variant", "mcs_plan_rows_need_padding", "mcs_plan_promise_padded_rows",
     "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_plan_tiled_stats", "mcs_launch_count",
     "mcs_match_hamming_top2", "mcs_match_l2_top2", "mcs_ransac_homography", "mcs_resize_linear_u8",
@@ -80,6 +80,9 @@ def load(build_if_missing=False):
     lib.mcs_copy_window_u8.restype = ctypes.c_int
     lib.mcs_copy_window_u8.argtypes = [_vp, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int64, ctypes.c_int64,
                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
+    lib.mcs_upload_pageable_u8.restype = ctypes.c_int
+    lib.mcs_upload_pageable_u8.argtypes = [ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                                           _c_i64p, _c_i64p, _c_i64p, ctypes.c_int64, ctypes.c_int, _vp]
     lib.mcs_stitch_u8.restype = ctypes.c_int
     lib.mcs_stitch_u8.argtypes = [_vp, ctypes.POINTER(_vp), _c_i64p, _c_i64p, ctypes.c_int, _vp,
                                   ctypes.c_int64, ctypes.c_int64, _vp]
@@ -145,6 +148,24 @@ def copy_window_u8(dst_ptr, dst_pitch, dst_frame_stride, src_ptr, src_pitch, src
     check(load().mcs_copy_window_u8(_vp(int(dst_ptr)), int(dst_pitch), int(dst_frame_stride), _vp(int(src_ptr)),
                                     int(src_pitch), int(src_frame_stride), int(x_byte0), int(width_bytes), int(y0),
                                     int(rows), int(n_frames), _vp(int(stream))), "mcs_copy_window_u8")
+
+
+def upload_pageable_u8(windows, piece_bytes, threads, stream=0):
+    """``windows``: (dst_ptr, src_ptr, staging_ptr, pitch, src_pitch, x_byte0, y0, width_bytes, rows) tuples
+    (include/mcs.h: mcs_upload_pageable_u8).  The GIL is released for the duration of the call."""
+    n = len(windows)
+    if n == 0:
+        return
+    arr = ctypes.c_void_p * n
+    dst = arr(*[int(w[0]) for w in windows])
+    src = arr(*[int(w[1]) for w in windows])
+    stg = arr(*[int(w[2]) for w in windows])
+    pitch = np.array([w[3] for w in windows], dtype=np.int64)
+    spitch = np.array([w[4] for w in windows], dtype=np.int64)
+    xywh = np.array([w[5:9] for w in windows], dtype=np.int64).reshape(-1)
+    check(load().mcs_upload_pageable_u8(n, dst, src, stg, pitch.ctypes.data_as(_c_i64p), spitch.ctypes.data_as(_c_i64p),
+                                        xywh.ctypes.data_as(_c_i64p), int(piece_bytes), int(threads), _vp(int(stream))),
+          "mcs_upload_pageable_u8")
 
 
 def _i32(a):

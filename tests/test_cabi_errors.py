@@ -46,6 +46,10 @@ def test_resize_and_copy_reject_bad_arguments_before_touching_the_device():
     assert lib.mcs_resize_linear_u8(None, 10, 10, 30, 0, None, 5, 5, 15, 0, 3, 1, None) == MCS_ERR_INVALID
     assert "NULL" in _last()
     assert lib.mcs_copy_window_u8(None, 64, 0, None, 64, 0, 0, 16, 0, 4, 1, None) == MCS_ERR_INVALID
+    assert lib.mcs_upload_pageable_u8(0, None, None, None, None, None, None, 0, 4, None) == 0     # no windows: nothing to do
+    assert lib.mcs_upload_pageable_u8(1, None, None, None, None, None, None, 0, 4, None) == MCS_ERR_INVALID
+    assert "NULL" in _last()
+    assert lib.mcs_upload_pageable_u8(-1, None, None, None, None, None, None, 0, 4, None) == MCS_ERR_INVALID
     assert lib.mcs_plan_source_windows(None, None) == MCS_ERR_INVALID
     assert lib.mcs_plan_set_feather(None, 1) == MCS_ERR_INVALID
     assert lib.mcs_plan_force_variant(None, 1) == MCS_ERR_INVALID
