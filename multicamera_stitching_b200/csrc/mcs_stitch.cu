@@ -165,6 +165,114 @@ mcs_stitch_gather_kernel(const __grid_constant__ StitchArgs a, unsigned long lon
 }
 
 // --------------------------------------------------------------------------------------------
+// Variant 1 as launched by mcs_stitch_u8: one thread per output pixel, consecutive lanes on
+// consecutive pixels, the frames of the launch looped INSIDE the thread.  Owner search and the
+// float64 coordinate recipe run once per pixel and launch, not once per pixel and frame; what is
+// left per frame is the twelve tap bytes (neighbouring lanes share their cache lines: a warp's 32
+// pixels read ~110 contiguous bytes per source row), the integer blend and C byte stores.  Same
+// arithmetic as sample_u8, byte loads and byte stores only: any pitch, any alignment.
+#ifndef MCS_GATHER_BX
+#define MCS_GATHER_BX 64
+#define MCS_GATHER_BY 4
+#endif
+#ifndef MCS_GATHER_FRAMES
+#define MCS_GATHER_FRAMES 16   // frames per thread (grid.z covers the rest)
+#endif
+#ifndef MCS_GATHER_UNROLL
+#define MCS_GATHER_UNROLL 1
+#endif
+
+// byte i (compile-time) of the 8-byte window (lo, hi)
+__device__ __forceinline__ int window_byte(uint32_t lo, uint32_t hi, int i) {
+    return (int)(((i < 4 ? lo : hi) >> (8 * (i & 3))) & 0xffu);
+}
+
+// WORDS: every source base, pitch and frame stride is a multiple of 4 bytes (checked by the launcher).  A pixel
+// whose four taps are inside the source, with another source row below them, then fetches its taps as aligned
+// 32-bit words (two or three per source row instead of 2 * C bytes) and realigns them with funnel shifts; such
+// loads never leave the rows of the frame.  Border pixels keep the byte loads.
+template <int C, bool WORDS>
+__global__ void __launch_bounds__(MCS_GATHER_BX * MCS_GATHER_BY)
+mcs_stitch_gather_frames_kernel(const __grid_constant__ StitchArgs a) {
+    const int x = blockIdx.x * MCS_GATHER_BX + threadIdx.x;
+    const int y = blockIdx.y * MCS_GATHER_BY + threadIdx.y;
+    if (x >= a.out_w || y >= a.out_h) return;
+    const int f0 = blockIdx.z * MCS_GATHER_FRAMES;
+    const int n_fr = min(MCS_GATHER_FRAMES, a.n_frames - f0);
+    uint8_t* out = a.dst + (long long)f0 * a.dst_frame_stride + (long long)y * a.dst_pitch + (long long)x * C;
+
+    const int k = find_owner(a, x, y);
+    if (k < 0) {   // background
+        for (int f = 0; f < n_fr; ++f, out += a.dst_frame_stride)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c] = 0;
+        return;
+    }
+    const LayerArgs& L = a.L[k];
+    const int xl = x - L.g.ox, yl = y - L.g.oy;
+    const uint8_t* src = L.src + (long long)f0 * L.frame_stride;
+    const long long fs = L.frame_stride;
+    if (L.g.kind == MCS_LAYER_COPY) {
+        const uint8_t* p = src + (long long)yl * L.pitch + (long long)xl * C;
+        for (int f = 0; f < n_fr; ++f, p += fs, out += a.dst_frame_stride) {
+            int v[C];
+            load_px<C>(p, v);
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c] = (uint8_t)v[c];
+        }
+        return;
+    }
+    int X, Y;
+    layer_coords(L.g, xl, yl, X, Y);
+    const int sx = sat16(X >> 5), sy = sat16(Y >> 5);
+    const int ax = X & 31, ay = Y & 31;
+    const bool x0in = (unsigned)sx < (unsigned)L.g.src_w, x1in = (unsigned)(sx + 1) < (unsigned)L.g.src_w;
+    const bool y0in = (unsigned)sy < (unsigned)L.g.src_h, y1in = (unsigned)(sy + 1) < (unsigned)L.g.src_h;
+    const bool t00 = y0in && x0in, t01 = y0in && x1in, t10 = y1in && x0in, t11 = y1in && x1in;
+    const int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32;
+    const int w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
+    const long long pitch = L.pitch;
+    const uint8_t* r0 = src + (long long)sy * pitch + (long long)sx * C;
+    if (!(t00 || t01 || t10 || t11)) {   // every tap outside the source: BORDER_CONSTANT 0
+        for (int f = 0; f < n_fr; ++f, out += a.dst_frame_stride)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c] = 0;
+        return;
+    }
+    if (WORDS && t00 && t11 && sy + 2 < L.g.src_h) {
+        const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(r0) & 3u), sh = phase * 8u;
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(r0 - phase);
+        const bool n1 = phase + 2 * C > 4, n2 = phase + 2 * C > 8;   // which words the 2 * C tap bytes reach
+        const long long pitch4 = pitch >> 2, fs4 = fs >> 2;
+        for (int f = 0; f < n_fr; ++f, q += fs4, out += a.dst_frame_stride) {
+            const uint32_t u0 = __ldg(q), u1 = n1 ? __ldg(q + 1) : 0u, u2 = n2 ? __ldg(q + 2) : 0u;
+            const uint32_t v0 = __ldg(q + pitch4), v1 = n1 ? __ldg(q + pitch4 + 1) : 0u, v2 = n2 ? __ldg(q + pitch4 + 2) : 0u;
+            const uint32_t lo0 = __funnelshift_r(u0, u1, sh), hi0 = __funnelshift_r(u1, u2, sh);
+            const uint32_t lo1 = __funnelshift_r(v0, v1, sh), hi1 = __funnelshift_r(v1, v2, sh);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                out[c] = (uint8_t)((w00 * window_byte(lo0, hi0, c) + w01 * window_byte(lo0, hi0, C + c) +
+                                    w10 * window_byte(lo1, hi1, c) + w11 * window_byte(lo1, hi1, C + c) + 16384) >> 15);
+        }
+        return;
+    }
+    constexpr int kUnroll = MCS_GATHER_UNROLL;
+#pragma unroll kUnroll
+    for (int f = 0; f < n_fr; ++f, r0 += fs, out += a.dst_frame_stride) {
+        int p00[C], p01[C], p10[C], p11[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) p00[c] = p01[c] = p10[c] = p11[c] = 0;
+        if (t00) load_px<C>(r0, p00);
+        if (t01) load_px<C>(r0 + C, p01);
+        if (t10) load_px<C>(r0 + pitch, p10);
+        if (t11) load_px<C>(r0 + pitch + C, p11);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            out[c] = (uint8_t)((w00 * p00[c] + w01 * p01[c] + w10 * p10[c] + w11 * p11[c] + 16384) >> 15);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
 // Feather blend mode (extension; the reference has only the overwrite
 // of StitcherClass.py:240-241).  Specification: oracle/feather_model.py.  The chain's nested
 // pastes are softened over F = 2^feather_log2 pixels inside every pasted rectangle:
@@ -359,6 +467,25 @@ static int fill_args(const mcs_plan* plan, StitchArgs& a, const uint8_t* const* 
     return MCS_OK;
 }
 
+static cudaError_t launch_gather_frames(const mcs_plan* plan, const StitchArgs& a, cudaStream_t stream) {
+    dim3 block(MCS_GATHER_BX, MCS_GATHER_BY, 1);
+    dim3 grid((plan->out_w + MCS_GATHER_BX - 1) / MCS_GATHER_BX, (plan->out_h + MCS_GATHER_BY - 1) / MCS_GATHER_BY,
+              (a.n_frames + MCS_GATHER_FRAMES - 1) / MCS_GATHER_FRAMES);
+    bool words = getenv("MCS_GATHER_BYTES") == nullptr;   // word-aligned sources: taps fetched as 32-bit words
+    for (int k = 0; k < a.n_layers; ++k)
+        words = words && ((reinterpret_cast<uintptr_t>(a.L[k].src) | (uintptr_t)a.L[k].pitch | (uintptr_t)a.L[k].frame_stride) & 3u) == 0;
+    switch (plan->channels * 2 + (words ? 1 : 0)) {
+        case 2: mcs_stitch_gather_frames_kernel<1, false><<<grid, block, 0, stream>>>(a); break;
+        case 3: mcs_stitch_gather_frames_kernel<1, true><<<grid, block, 0, stream>>>(a); break;
+        case 6: mcs_stitch_gather_frames_kernel<3, false><<<grid, block, 0, stream>>>(a); break;
+        case 7: mcs_stitch_gather_frames_kernel<3, true><<<grid, block, 0, stream>>>(a); break;
+        case 8: mcs_stitch_gather_frames_kernel<4, false><<<grid, block, 0, stream>>>(a); break;
+        default: mcs_stitch_gather_frames_kernel<4, true><<<grid, block, 0, stream>>>(a); break;
+    }
+    mcs_count_launch(1);
+    return cudaGetLastError();
+}
+
 template <bool STATS>
 static cudaError_t launch_gather(const mcs_plan* plan, const StitchArgs& a, unsigned long long* owned,
                                  cudaStream_t stream) {
@@ -409,7 +536,10 @@ extern "C" int mcs_stitch_u8(const mcs_plan* plan_c, const uint8_t* const* src,
     } else {
         fill_args(plan, a, src, src_pitch_bytes, src_frame_stride, n_frames, dst, dst_pitch_bytes,
                   dst_frame_stride);
-        MCS_CHECK_CUDA(launch_gather<false>(plan, a, nullptr, stream));
+        if (getenv("MCS_GATHER_LEGACY"))   // the four-pixels-per-thread, frame-per-CTA form (experiments)
+            MCS_CHECK_CUDA(launch_gather<false>(plan, a, nullptr, stream));
+        else
+            MCS_CHECK_CUDA(launch_gather_frames(plan, a, stream));
         plan->last_variant = 1;
     }
     if (plan->band_fused && plan->last_variant == 2) {

@@ -452,3 +452,31 @@ def test_frame_counts_whose_last_block_is_shorter_than_the_split(cuda_device, n_
     assert plan.handle.last_variant() == 2
     want = torch.from_numpy(ref).to(cuda_device)
     assert bool((out == want[None]).all())
+
+
+@pytest.mark.parametrize("n,h,w,c,super_mode", [(3, 97, 131, 3, False), (3, 96, 132, 3, False), (4, 120, 200, 1, False),
+                                                  (3, 90, 160, 4, True)])
+def test_gather_variant_batches(cuda_device, monkeypatch, n, h, w, c, super_mode):
+    """The fallback kernel loops the frames of a launch inside its threads (16 per thread, the rest through
+    grid.z): batches around that block size, frame by frame against the cv2 chain - with rows that are and are
+    not multiples of four bytes (aligned word loads or byte loads for the taps), with the byte loads forced
+    ($MCS_GATHER_BYTES), and through the older frame-per-CTA form kept behind $MCS_GATHER_LEGACY."""
+    st, states, labels, images = synthetic_chain(n, h, w, c, kind="noise", super_mode=super_mode)
+    plan = st.plan([images[l].shape for l in labels], cuda_device)
+    try:
+        plan.handle.force_variant(1)
+        for F in (1, 15, 16, 17, 35):
+            sets = [synthetic_chain(n, h, w, c, kind="noise", super_mode=super_mode, frame_index=f % 5)[3] for f in range(F)]
+            batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
+            refs = [stitcher_ref.stitch_chain(states, labels, sets[f]) for f in range(min(F, 5))]
+            for mode in ("", "MCS_GATHER_BYTES", "MCS_GATHER_LEGACY"):
+                monkeypatch.delenv("MCS_GATHER_LEGACY", raising=False)
+                monkeypatch.delenv("MCS_GATHER_BYTES", raising=False)
+                if mode:
+                    monkeypatch.setenv(mode, "1")
+                out = st.stitch_batch(batch).cpu().numpy()
+                assert plan.handle.last_variant() == 1
+                for f in range(F):
+                    assert np.array_equal(out[f], refs[f % 5]), (F, f, mode)
+    finally:
+        plan.handle.force_variant(0)
