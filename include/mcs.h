@@ -362,6 +362,21 @@ int mcs_ransac_homography(const float* ptsA, const float* ptsB, const int32_t* n
                           double* H_k, int32_t* best_idx, uint8_t* best_mask,
                           int batch, void* cuda_stream);
 
+/*
+ * mcs_refit_homography - the host end of cv2.findHomography(ptsA, ptsB, RANSAC, reprojThresh)
+ * (StitcherClass.py:443-444): least-squares refit of the winning hypothesis on its inliers
+ * (normalised DLT) followed by lm_iters Levenberg-Marquardt iterations on the reprojection error
+ * (OpenCV: 10).  Plain host code, no device, no stream.
+ *
+ *   pts_a, pts_b   host float32 [n][2] matched points (A -> B)
+ *   inlier_mask    host uint8 [n] (non-zero = inlier) or NULL (= all points)
+ *   h0             host float64 [9]: the winning hypothesis; returned unchanged with fewer than 4
+ *                  inliers, used as the starting point with exactly 4 or when the DLT degenerates
+ *   h_out          host float64 [9], h_out[8] == 1 after a refit
+ */
+int mcs_refit_homography(const float* pts_a, const float* pts_b, const uint8_t* inlier_mask, int n,
+                         const double* h0, int lm_iters, double* h_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ EXPORTS = (
     "mcs_plan_owned_pixels", "mcs_plan_source_windows", "mcs_plan_source_spans", "mcs_copy_window_u8", "mcs_upload_pageable_u8", "mcs_stitch_u8", "mcs_plan_set_feather", "mcs_plan_set_blend", "mcs_plan_last_variant",
     "mcs_plan_force_variant", "mcs_plan_rows_need_padding", "mcs_plan_promise_padded_rows",
     "mcs_plan_tiled_status", "mcs_plan_tiled_ctas_per_sm", "mcs_plan_tiled_stats", "mcs_launch_count",
-    "mcs_match_hamming_top2", "mcs_match_l2_top2", "mcs_ransac_homography", "mcs_resize_linear_u8",
+    "mcs_match_hamming_top2", "mcs_match_l2_top2", "mcs_ransac_homography", "mcs_refit_homography", "mcs_resize_linear_u8",
 )
 
 
@@ -83,6 +83,8 @@ def load(build_if_missing=False):
     lib.mcs_upload_pageable_u8.restype = ctypes.c_int
     lib.mcs_upload_pageable_u8.argtypes = [ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
                                            _c_i64p, _c_i64p, _c_i64p, ctypes.c_int64, ctypes.c_int, _vp]
+    lib.mcs_refit_homography.restype = ctypes.c_int
+    lib.mcs_refit_homography.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp]
     lib.mcs_stitch_u8.restype = ctypes.c_int
     lib.mcs_stitch_u8.argtypes = [_vp, ctypes.POINTER(_vp), _c_i64p, _c_i64p, ctypes.c_int, _vp,
                                   ctypes.c_int64, ctypes.c_int64, _vp]
@@ -166,6 +168,24 @@ def upload_pageable_u8(windows, piece_bytes, threads, stream=0):
     check(load().mcs_upload_pageable_u8(n, dst, src, stg, pitch.ctypes.data_as(_c_i64p), spitch.ctypes.data_as(_c_i64p),
                                         xywh.ctypes.data_as(_c_i64p), int(piece_bytes), int(threads), _vp(int(stream))),
           "mcs_upload_pageable_u8")
+
+
+def refit_homography(pts_a, pts_b, mask, h0, lm_iters=10):
+    """Inlier refit + LM polish of a RANSAC winner on the host (include/mcs.h: mcs_refit_homography).
+    ``pts_a`` / ``pts_b``: float32 N x 2, ``mask``: uint8 N or None, ``h0``: 3 x 3.  Returns H 3 x 3 float64."""
+    a = np.ascontiguousarray(pts_a, dtype=np.float32).reshape(-1, 2)
+    b = np.ascontiguousarray(pts_b, dtype=np.float32).reshape(-1, 2)
+    if len(a) != len(b):
+        raise ValueError("point sets differ in length: %d and %d" % (len(a), len(b)))
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
+    if m is not None and len(m) != len(a):
+        raise ValueError("mask length %d for %d points" % (len(m), len(a)))
+    h = np.ascontiguousarray(h0, dtype=np.float64).reshape(9)
+    out = np.empty(9, dtype=np.float64)
+    check(load().mcs_refit_homography(_vp(a.ctypes.data), _vp(b.ctypes.data), _vp(m.ctypes.data if m is not None else 0),
+                                      len(a), _vp(h.ctypes.data), int(lm_iters), _vp(out.ctypes.data)),
+          "mcs_refit_homography")
+    return out.reshape(3, 3)
 
 
 def _i32(a):

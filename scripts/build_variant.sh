@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 out=multicamera_stitching_b200/build/variants
 mkdir -p $out/$name
-for f in mcs_plan mcs_tiles mcs_stitch mcs_stitch_tiled mcs_match mcs_ransac mcs_resize mcs_hostio; do
+for f in mcs_plan mcs_tiles mcs_stitch mcs_stitch_tiled mcs_match mcs_ransac mcs_resize mcs_hostio mcs_refit; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=false \
        -Xcompiler -fPIC,-O2,-ffp-contract=off -Xptxas -v -I include -I multicamera_stitching_b200/csrc "$@" \
        -c multicamera_stitching_b200/csrc/$f.cu -o $out/$name/$f.o > $out/$name/$f.log 2>&1 &
