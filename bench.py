@@ -160,18 +160,33 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------
-def time_cpu_chain(states, labels, frame_sets, budget_s, min_panos=4, threads=None):
-    """Reference CPU path: the sequential cv2 chain of StitcherClass.py:131-136."""
+def cpu_chain_runner(states, labels, images, homographies):
+    """``(run(frame_set) -> panorama, kind, description)`` of the CPU arm: the reference's own ``Stitcher`` class where
+    oracle/_ref exists (``kind`` "reference"), else the cv2 restatement of its chain (``kind`` "port")."""
     import cv2
-    from oracle import stitcher_ref
+    from oracle import build_ref, stitcher_ref
+    ref_mod = None if os.environ.get("MCS_BENCH_REFERENCE_PORT") else build_ref.load()
+    if ref_mod is not None:
+        rs = build_ref.calibrated_stitcher(ref_mod, images, homographies)
+        return (lambda fs: rs.stitch(fs)), "reference", (
+            "the reference's own Stitcher.stitch (StitcherClass.py:114-136 through oracle/_ref, built by "
+            "oracle/build_ref.py), cv2 %s" % cv2.__version__)
+    return (lambda fs: stitcher_ref.stitch_chain(states, labels, fs)), "port", (
+        "cv2 %s chain (warpPerspective + paste, StitcherClass.py:131-136, :239-241; oracle/stitcher_ref.py, pinned "
+        "against the reference's own StitcherClass.py by tests/test_oracle_ref_pin.py)" % cv2.__version__)
+
+
+def time_cpu_chain(run, frame_sets, budget_s, min_panos=4, threads=None):
+    """Reference CPU path: the sequential cv2 chain of StitcherClass.py:131-136 (``run`` from cpu_chain_runner)."""
+    import cv2
     if threads is not None:
         cv2.setNumThreads(threads)
     for fs in frame_sets[:2]:
-        stitcher_ref.stitch_chain(states, labels, fs)  # warm-up
+        run(fs)  # warm-up
     n = 0
     t0 = time.perf_counter()
     while True:
-        stitcher_ref.stitch_chain(states, labels, frame_sets[n % len(frame_sets)])
+        run(frame_sets[n % len(frame_sets)])
         n += 1
         dt = time.perf_counter() - t0
         if (dt >= budget_s and n >= min_panos) or n >= 100000:
@@ -187,24 +202,32 @@ def make_frame_sets_offset(name, count, first_frame):
 
 # ---------------------------------------------------------------------------
 def run_reference(args, rank, world):
+    """The reference arm: the reference's OWN ``Stitcher`` class (PostScripts/Stitcher/StitcherClass.py, made
+    importable by oracle/build_ref.py -> oracle/_ref, a build output that travels to the GPU box) calibrated with the
+    workload's stage homographies and timed through its own ``stitch(images_dic)`` on all host threads.  Where
+    that build output is missing, the cv2 restatement of the same chain (oracle/stitcher_ref.py) is timed."""
     if rank != 0:
         return
     st, homographies, labels, images = build_chain(args.workload)
-    states = oracle_states(homographies, labels, images)
     frame_sets = make_frame_sets_offset(args.workload, 4, 0)
     import cv2
     from oracle import stitcher_ref
     cv2.setNumThreads(os.cpu_count() or 1)
-    ref = stitcher_ref.stitch_chain(states, labels, frame_sets[0])
+    states = oracle_states(homographies, labels, images)
+    check = stitcher_ref.stitch_chain(states, labels, frame_sets[0])
+    run, kind, what = cpu_chain_runner(states, labels, images, homographies)
+    ref = run(frame_sets[0])
+    if not np.array_equal(ref, check):
+        raise SystemExit("bench.py: the reference arm and its restatement disagree")
     out_h, out_w = ref.shape[:2]
     per_step = args.ref_panos_per_step
     for _ in range(args.warmup):
         for i in range(per_step):
-            stitcher_ref.stitch_chain(states, labels, frame_sets[i % 4])
+            run(frame_sets[i % 4])
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for i in range(per_step):
-            stitcher_ref.stitch_chain(states, labels, frame_sets[i % 4])
+            run(frame_sets[i % 4])
     dt = time.perf_counter() - t0
     pps = args.steps * per_step / dt
     line = {
@@ -216,11 +239,9 @@ def run_reference(args, rank, world):
         "config": {"workload": args.workload, "cameras": WORKLOADS[args.workload][0],
                    "frame_hw": list(WORKLOADS[args.workload][1:3]), "panorama_wh": [out_w, out_h],
                    "panoramas_per_step": per_step},
-        "cpu_baseline": {"value": pps, "unit": "panoramas/s", "cores": cv2.getNumThreads(), "kind": "port",
-                         "sample": "%d steps x %d panoramas, cv2 %s chain (warpPerspective + paste, "
-                                   "StitcherClass.py:131-136, :239-241; oracle/stitcher_ref.py, pinned against the "
-                                   "reference's own StitcherClass.py by tests/test_oracle_ref_pin.py), %d threads"
-                                   % (args.steps, per_step, cv2.__version__, cv2.getNumThreads())},
+        "cpu_baseline": {"value": pps, "unit": "panoramas/s", "cores": cv2.getNumThreads(), "kind": kind,
+                         "sample": "%d steps x %d panoramas, %s, %d threads"
+                                   % (args.steps, per_step, what, cv2.getNumThreads())},
         "e2e": {"value": pps, "unit": "panoramas/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -628,13 +649,13 @@ def run_ours(args, rank, local_rank, world):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import cv2
-        cpu_pps, n, dt, threads = time_cpu_chain(states, w.labels, w.ring[:4], args.cpu_budget * 0.75,
-                                                 threads=os.cpu_count() or 1)
-        one_pps, _, _, _ = time_cpu_chain(states, w.labels, w.ring[:4], args.cpu_budget * 0.25, min_panos=2, threads=1)
-        cpu = {"value": cpu_pps, "unit": "panoramas/s", "cores": threads, "single_thread_value": one_pps, "kind": "port",
-               "sample": "%d panoramas of %s in %.1f s: cv2 %s warpPerspective+paste chain (oracle/stitcher_ref.py, "
-                         "StitcherClass.py:131-136; pinned against the reference's own StitcherClass.py by "
-                         "tests/test_oracle_ref_pin.py), %d threads" % (n, args.workload, dt, cv2.__version__, threads)}
+        run_cpu, kind, what = cpu_chain_runner(states, w.labels, w.images, w.homographies)
+        if not np.array_equal(run_cpu(w.ring[0]), ref):
+            raise SystemExit("bench.py: the CPU arm and its restatement disagree")
+        cpu_pps, n, dt, threads = time_cpu_chain(run_cpu, w.ring[:4], args.cpu_budget * 0.75, threads=os.cpu_count() or 1)
+        one_pps, _, _, _ = time_cpu_chain(run_cpu, w.ring[:4], args.cpu_budget * 0.25, min_panos=2, threads=1)
+        cpu = {"value": cpu_pps, "unit": "panoramas/s", "cores": threads, "single_thread_value": one_pps, "kind": kind,
+               "sample": "%d panoramas of %s in %.1f s: %s, %d threads" % (n, args.workload, dt, what, threads)}
 
     in_bytes, out_numel, out_pitch = w.in_bytes, int(w.out.numel()), int(w.out.stride(1))
     algo_bytes = w.algo_bytes

@@ -7,7 +7,8 @@ compile (mixed space + tab indentation of ``__str__``, ``np.sort(dict.keys())``)
 the repository does not ship.  This recipe reads the file WHERE IT LIES, applies the mechanical patch list
 below - nothing that touches the arithmetic of the stitch / geometry / match path - and writes the result to
 ``oracle/_ref/StitcherClass_ref.py`` next to a stand-in ``extended_rospylogs.py``.  The reference's
-``Calibration_Utils/Utils.py`` is imported UNCHANGED from the reference tree (it runs under Python 3 as is).
+``Calibration_Utils/Utils.py`` is imported UNCHANGED from the reference tree (it runs under Python 3 as is); a byte
+copy of it is placed in the build output for the GPU box, which has no reference tree (``prebuilt()``).
 No reference source is copied into the repository: ``oracle/_ref/`` is a build output, like a ``.so``.
 
 The patched module is what ``tests/test_oracle_ref_pin.py`` holds ``oracle/stitcher_ref.py`` against and what
@@ -90,20 +91,57 @@ def build(verbose=False):
         f.write(header + src)
     with open(os.path.join(OUT_DIR, "extended_rospylogs.py"), "w") as f:
         f.write(SHIM)
+    # The GPU box has no /root/reference: the helper module the class imports travels with the build output,
+    # byte for byte as it lies in the reference tree (used only where that tree is absent, see load()).
+    os.makedirs(os.path.join(OUT_DIR, "Calibration_Utils"), exist_ok=True)
+    with open(os.path.join(REF_UTILS_DIR, "Utils.py"), "rb") as f, \
+            open(os.path.join(OUT_DIR, "Calibration_Utils", "Utils.py"), "wb") as g:
+        g.write(f.read())
     compile(src, out, "exec")   # fails here, loudly, if the patch list no longer makes it Python 3
     return out
+
+
+def prebuilt():
+    """The build output of an earlier run (it travels to the GPU box, the reference tree does not)."""
+    out = os.path.join(OUT_DIR, "StitcherClass_ref.py")
+    ok = os.path.isfile(out) and os.path.isfile(os.path.join(OUT_DIR, "extended_rospylogs.py")) and \
+        os.path.isfile(os.path.join(OUT_DIR, "Calibration_Utils", "Utils.py"))
+    return out if ok else None
 
 
 def load():
     """Imports the patched reference module (building it first); None when the reference is absent."""
     path = build()
+    utils_dir = REF_UTILS_DIR
+    if path is None:
+        path = prebuilt()
+        utils_dir = os.path.join(OUT_DIR, "Calibration_Utils")
     if path is None:
         return None
-    for p in (OUT_DIR, REF_UTILS_DIR):
+    for p in (OUT_DIR, utils_dir):
         if p not in sys.path:
             sys.path.insert(0, p)
     import importlib
     return importlib.import_module("StitcherClass_ref")
+
+
+def calibrated_stitcher(ref, images_dic, homographies, super_mode=False):
+    """The reference's own ``Stitcher`` (``ref`` = the module from ``load()``), calibrated by its own
+    ``calibrate_stitcher`` (StitcherClass.py:77-112) with the given stage homographies standing in for matched
+    features: ``StitcherBase.calibrate`` (:258-354) runs its real geometry code, only the feature detection and
+    matching in front of it are replaced.  Every stage calibrates against the stitched canvas so far."""
+    import numpy as np
+    rs = ref.Stitcher(images_dic, super_mode=super_mode)
+
+    def fixed(H):
+        H = np.array(H, dtype=np.float64)
+        return lambda *a, **kw: (H.copy(), [(0, 0)] * 5, np.ones((5, 1), np.uint8))
+
+    for sb, H in zip(rs.stitchers, homographies):
+        sb.detectAndDescribe = lambda image: (np.zeros((1, 2), np.float32), None)
+        sb.matchKeypoints = fixed(H)
+    rs.calibrate_stitcher(images_dic, save=False)
+    return rs
 
 
 if __name__ == "__main__":

@@ -255,3 +255,33 @@ def test_per_stage_overlays_equal_the_reference(ref, n, super_mode):
     st.plan = lambda shapes, device=None: p
     got = st._draw_overlays(base, [images[l] for l in labels])
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_prebuilt_reference_runs_without_the_reference_tree(tmp_path):
+    """The build output (oracle/_ref: the patched class, the logging stand-in, a byte copy of the reference's
+    Utils.py) is all the GPU box has: with the reference tree out of reach, ``build_ref.load()`` falls back to it
+    and the reference's own ``Stitcher`` still produces the panorama of the restatement - this is the CPU arm of
+    ``bench.py --impl reference`` there."""
+    import subprocess
+    import sys
+    assert build_ref.build() is not None
+    with open(os.path.join(build_ref.REF_UTILS_DIR, "Utils.py"), "rb") as f, \
+            open(os.path.join(build_ref.OUT_DIR, "Calibration_Utils", "Utils.py"), "rb") as g:
+        assert f.read() == g.read()
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from helpers import synthetic_chain\n"
+        "from multicamera_stitching_b200 import synthetic\n"
+        "from oracle import build_ref, stitcher_ref\n"
+        "assert not build_ref.available() and build_ref.prebuilt()\n"
+        "ref = build_ref.load()\n"
+        "st, hs, labels, images = synthetic.synthetic_stitcher(4, 90, 160, 3, kind='noise')\n"
+        "states = stitcher_ref.calibrate_chain_from_homographies([images[l].shape for l in labels], hs)\n"
+        "rs = build_ref.calibrated_stitcher(ref, images, hs)\n"
+        "assert np.array_equal(rs.stitch(images), stitcher_ref.stitch_chain(states, labels, images))\n"
+        "print('prebuilt ok')\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, MCS_REFERENCE_ROOT=str(tmp_path / "no_reference_here"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    assert r.returncode == 0 and b"prebuilt ok" in r.stdout, r.stdout.decode(errors="replace")
