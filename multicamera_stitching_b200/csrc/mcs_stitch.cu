@@ -241,18 +241,24 @@ mcs_stitch_gather_frames_kernel(const __grid_constant__ StitchArgs a) {
     }
     if (WORDS && t00 && t11 && sy + 2 < L.g.src_h) {
         const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(r0) & 3u), sh = phase * 8u;
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(r0 - phase);
+        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(r0 - phase);   // upper tap row
+        const uint32_t* q1 = q0 + (pitch >> 2);                               // lower tap row
         const bool n1 = phase + 2 * C > 4, n2 = phase + 2 * C > 8;   // which words the 2 * C tap bytes reach
-        const long long pitch4 = pitch >> 2, fs4 = fs >> 2;
-        for (int f = 0; f < n_fr; ++f, q += fs4, out += a.dst_frame_stride) {
-            const uint32_t u0 = __ldg(q), u1 = n1 ? __ldg(q + 1) : 0u, u2 = n2 ? __ldg(q + 2) : 0u;
-            const uint32_t v0 = __ldg(q + pitch4), v1 = n1 ? __ldg(q + pitch4 + 1) : 0u, v2 = n2 ? __ldg(q + pitch4 + 2) : 0u;
+        const long long fs4 = fs >> 2;
+        // tap weights as 16-bit pairs for IDP.2A (32768 = 32 * 32 * 32 fits an unsigned half)
+        const uint32_t wu = (uint32_t)w00 | ((uint32_t)w01 << 16), wl = (uint32_t)w10 | ((uint32_t)w11 << 16);
+        for (int f = 0; f < n_fr; ++f, q0 += fs4, q1 += fs4, out += a.dst_frame_stride) {
+            const uint32_t u0 = __ldg(q0), u1 = n1 ? __ldg(q0 + 1) : 0u, u2 = n2 ? __ldg(q0 + 2) : 0u;
+            const uint32_t v0 = __ldg(q1), v1 = n1 ? __ldg(q1 + 1) : 0u, v2 = n2 ? __ldg(q1 + 2) : 0u;
             const uint32_t lo0 = __funnelshift_r(u0, u1, sh), hi0 = __funnelshift_r(u1, u2, sh);
             const uint32_t lo1 = __funnelshift_r(v0, v1, sh), hi1 = __funnelshift_r(v1, v2, sh);
 #pragma unroll
-            for (int c = 0; c < C; ++c)
-                out[c] = (uint8_t)((w00 * window_byte(lo0, hi0, c) + w01 * window_byte(lo0, hi0, C + c) +
-                                    w10 * window_byte(lo1, hi1, c) + w11 * window_byte(lo1, hi1, C + c) + 16384) >> 15);
+            for (int c = 0; c < C; ++c) {
+                // bytes c and C + c of the 8-byte window (lo, hi): the two taps of channel c in this row
+                const uint32_t sel = (uint32_t)c | ((uint32_t)(C + c) << 4);   // IDP.2A.LO reads bytes 0 and 1 only
+                const uint32_t tu = __byte_perm(lo0, hi0, sel), tl = __byte_perm(lo1, hi1, sel);
+                out[c] = (uint8_t)(__dp2a_lo(wl, tl, __dp2a_lo(wu, tu, 16384u)) >> 15);
+            }
         }
         return;
     }
