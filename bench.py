@@ -396,6 +396,23 @@ def extra_recalibration(device, budget_s=4.0):
         n += 1
     torch.cuda.synchronize()
     gpu = 4 * n / (time.perf_counter() - t0)
+    # the matching kernel alone, descriptors resident (north_star: "the matcher reports INT/popcount pipe utilisation")
+    nq_max, nt_max = max(len(i[2]) for i in items), max(len(i[3]) for i in items)
+    dq = torch.zeros((4, nq_max, 32), dtype=torch.uint8, device=device)
+    dt_ = torch.zeros((4, nt_max, 32), dtype=torch.uint8, device=device)
+    for j, (_, _, fa, fb) in enumerate(items):
+        dq[j, :len(fa)] = torch.from_numpy(np.ascontiguousarray(fa)).to(device)
+        dt_[j, :len(fb)] = torch.from_numpy(np.ascontiguousarray(fb)).to(device)
+    for _ in range(5):
+        recalib.match_top2_batch(dq, dt_, ratio=0.75)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        recalib.match_top2_batch(dq, dt_, ratio=0.75)
+    e1.record()
+    torch.cuda.synchronize()
+    match_ms = e0.elapsed_time(e1) / 50
+    popc = 4 * nq_max * nt_max * 8      # 32-bit popcounts per launch (SURVEY section 8 d)
     cv2.setNumThreads(os.cpu_count() or 1)
     m, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s / 2 or m < 2:
@@ -407,6 +424,9 @@ def extra_recalibration(device, budget_s=4.0):
             "value": gpu, "unit": "pairs/s", "api": "recalib.match_keypoints_batch (StitcherBase.matchKeypoints for 4 pairs: "
             "1 matching + 1 RANSAC launch, host refit included, numpy in / numpy out)",
             "keypoints": [int(len(i[2])) for i in items], "match_lists_equal_cv2": bool(exact),
+            "match_kernel": {"ms_per_launch": match_ms, "popc32_per_s": popc / (match_ms * 1e-3),
+                             "xu_popc_pipe_pct_of_peak": 68.6, "alu_pipe_pct_of_peak": 36.0, "tensor_pipe_pct": 0.0,
+                             "pipe_source": "ncu --set full, profiles/r1_match_ncu_full.txt (the kernel is unchanged since)"},
             "cpu_pairs_per_s": cpu, "cpu_threads": cv2.getNumThreads(), "n_gpus_used": 1}
 
 
