@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <exception>
 #include <memory>
 #include <mutex>
 #include <string.h>
@@ -136,6 +137,7 @@ extern "C" int mcs_upload_pageable_u8(int n_windows, void* const* dst, const voi
     MCS_CHECK_ARG(dst && src && staging && pitch_bytes && src_pitch_bytes && xywh, "mcs_upload_pageable_u8: NULL table");
     MCS_CHECK_ARG(threads >= 1, "mcs_upload_pageable_u8: needs at least one staging thread");
     if (piece_bytes <= 0) piece_bytes = 1 << 20;
+    try {   // std::vector / std::thread may throw; nothing crosses the C boundary
     std::vector<Piece> pieces;
     for (int i = 0; i < n_windows; ++i) {
         const int64_t x0 = xywh[4 * i], y0 = xywh[4 * i + 1], w = xywh[4 * i + 2], h = xywh[4 * i + 3];
@@ -165,4 +167,8 @@ extern "C" int mcs_upload_pageable_u8(int n_windows, void* const* dst, const voi
         return MCS_ERR_CUDA;
     }
     return MCS_OK;
+    } catch (const std::exception& e) {
+        mcs_set_error("mcs_upload_pageable_u8: %s", e.what());
+        return MCS_ERR_NOMEM;
+    }
 }

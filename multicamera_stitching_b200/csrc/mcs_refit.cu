@@ -7,6 +7,7 @@
 // accumulation, no allocation proportional to anything but the inlier count.
 #include "mcs_common.h"
 
+#include <exception>
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -238,6 +239,7 @@ extern "C" int mcs_refit_homography(const float* pts_a, const float* pts_b, cons
     MCS_CHECK_ARG(n >= 0 && lm_iters >= 0, "mcs_refit_homography: negative count");
     MCS_CHECK_ARG(h0 != nullptr && h_out != nullptr, "mcs_refit_homography: NULL homography");
     MCS_CHECK_ARG(n == 0 || (pts_a != nullptr && pts_b != nullptr), "mcs_refit_homography: NULL points");
+    try {   // std::vector may throw; nothing crosses the C boundary
     std::vector<double> a, b;
     a.reserve(2 * (size_t)n);
     b.reserve(2 * (size_t)n);
@@ -258,4 +260,8 @@ extern "C" int mcs_refit_homography(const float* pts_a, const float* pts_b, cons
     }
     memcpy(h_out, H, sizeof(H));
     return MCS_OK;
+    } catch (const std::exception& e) {
+        mcs_set_error("mcs_refit_homography: %s", e.what());
+        return MCS_ERR_NOMEM;
+    }
 }
