@@ -108,6 +108,12 @@ def test_staged_uploads(cuda_device, monkeypatch, threads):
         mixed = dict(imgs)
         mixed[labels[1]] = torch.from_numpy(imgs[labels[1]])   # a CPU tensor among numpy frames
         assert np.array_equal(np.asarray(st.stitch(mixed)), ref)
+        # views whose rows are not dense (channels reversed) or run backwards (flipped): staged through a copy
+        swapped = {l: imgs[l][:, :, ::-1] for l in labels}
+        flipped = {l: imgs[l][::-1] for l in labels}
+        for views in (swapped, flipped):
+            want = stitcher_ref.stitch_chain(states, labels, {l: np.ascontiguousarray(v) for l, v in views.items()})
+            assert np.array_equal(st.stitch(views), want)
 
 
 def test_staging_threads_copy_the_windows_without_a_device():
