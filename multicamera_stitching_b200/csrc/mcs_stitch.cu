@@ -182,11 +182,6 @@ mcs_stitch_gather_kernel(const __grid_constant__ StitchArgs a, unsigned long lon
 #define MCS_GATHER_UNROLL 1
 #endif
 
-// byte i (compile-time) of the 8-byte window (lo, hi)
-__device__ __forceinline__ int window_byte(uint32_t lo, uint32_t hi, int i) {
-    return (int)(((i < 4 ? lo : hi) >> (8 * (i & 3))) & 0xffu);
-}
-
 // WORDS: every source base, pitch and frame stride is a multiple of 4 bytes (checked by the launcher).  A pixel
 // whose four taps are inside the source, with another source row below them, then fetches its taps as aligned
 // 32-bit words (two or three per source row instead of 2 * C bytes) and realigns them with funnel shifts; such

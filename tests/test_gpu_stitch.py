@@ -470,13 +470,15 @@ def test_gather_variant_batches(cuda_device, monkeypatch, n, h, w, c, super_mode
             batch = {l: torch.from_numpy(np.stack([s[l] for s in sets])).to(cuda_device) for l in labels}
             refs = [stitcher_ref.stitch_chain(states, labels, sets[f]) for f in range(min(F, 5))]
             for mode in ("", "MCS_GATHER_BYTES", "MCS_GATHER_LEGACY"):
-                monkeypatch.delenv("MCS_GATHER_LEGACY", raising=False)
-                monkeypatch.delenv("MCS_GATHER_BYTES", raising=False)
+                for k in ("MCS_GATHER_LEGACY", "MCS_GATHER_BYTES"):
+                    monkeypatch.delenv(k, raising=False)
                 if mode:
                     monkeypatch.setenv(mode, "1")
-                out = st.stitch_batch(batch).cpu().numpy()
-                assert plan.handle.last_variant() == 1
-                for f in range(F):
-                    assert np.array_equal(out[f], refs[f % 5]), (F, f, mode)
+                # dense panorama rows, and rows padded to a multiple of four bytes
+                for out in (None, plan.new_output(F, pitch_align=4)):
+                    got = st.stitch_batch(batch, out=out).cpu().numpy()
+                    assert plan.handle.last_variant() == 1
+                    for f in range(F):
+                        assert np.array_equal(got[f], refs[f % 5]), (F, f, mode, out is None)
     finally:
         plan.handle.force_variant(0)
