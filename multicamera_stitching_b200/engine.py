@@ -44,7 +44,8 @@ class PinnedResults(object):
         self.budget = int(os.environ.get("MCS_PINNED_RESULT_BYTES", str(512 << 20))) if budget is None else int(budget)
         self._free = {}     # shape -> [pinned tensors]
         self._bytes = 0     # pinned bytes allocated, handed out or free
-        self._lock = threading.Lock()
+        # re-entrant: a garbage collection that starts inside take() may finalise a result array on this very thread
+        self._lock = threading.RLock()
 
     def take(self, shape):
         """A pinned uint8 tensor of this shape, or None when the budget is spent."""
