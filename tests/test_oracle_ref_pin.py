@@ -177,6 +177,41 @@ def test_random_chains_equal_reference(ref):
         assert np.array_equal(rs.stitch(images), stitcher_ref.stitch_chain(states, labels, images))
 
 
+@pytest.mark.parametrize("super_mode", [False, True])
+def test_random_chains_sweep_equals_reference(ref, super_mode):
+    """A wider seeded sweep of the same fuzz geometry - 2 to 6 cameras, odd frame sizes, super mode, calibration
+    offsets - states and panoramas equal to the reference's, or both sides refusing the geometry alike."""
+    compared = 0
+    for seed in range(40):
+        rng = np.random.default_rng(7000 + seed)
+        n = int(rng.integers(2, 7))
+        h, w = int(rng.integers(40, 100)), int(rng.integers(50, 140))
+        images = synthetic.make_frames(n, h, w, 3, frame_index=seed, kind="noise")
+        labels = stitcher_ref.sorted_labels(images)
+        homs = random_homographies(n - 1, h, w, seed=500 + seed)
+        shapes = [images[l].shape for l in labels]
+        try:
+            rs = reference_chain(ref, images, homs, super_mode)
+        except (ValueError, cv2.error) as e:
+            with pytest.raises(type(e)):
+                states = stitcher_ref.calibrate_chain_from_homographies(shapes, homs, super_mode=super_mode)
+                stitcher_ref.stitch_chain(states, labels, images)
+            continue
+        states = stitcher_ref.calibrate_chain_from_homographies(shapes, homs, super_mode=super_mode)
+        for sb, s in zip(rs.stitchers, states):
+            assert_state_equal(sb, s)
+        try:
+            want = rs.stitch(images)
+        except (ValueError, cv2.error) as e:
+            with pytest.raises(type(e)):
+                stitcher_ref.stitch_chain(states, labels, images)
+            continue
+        got = stitcher_ref.stitch_chain(states, labels, images)
+        assert got.shape == want.shape and np.array_equal(got, want), seed
+        compared += 1
+    assert compared >= 20, compared
+
+
 # ---- a5: matchKeypoints (StitcherClass.py:405-448), the reference's own float / L2 branch -----------------
 def test_match_keypoints_equals_reference(ref):
     rng = np.random.default_rng(3)
