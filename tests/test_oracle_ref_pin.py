@@ -82,6 +82,27 @@ def test_geometry_equals_reference_calibrate(ref, offsets):
         assert_state_equal(sb, st)
 
 
+@pytest.mark.parametrize("offsets", [(0, 0), (10, 10), (-7, 4)])
+@pytest.mark.parametrize("super_mode", [False, True])
+def test_product_geometry_equals_reference_calibrate(ref, offsets, super_mode):
+    """The PRODUCT's own host-side geometry (``StitcherBase.set_homography`` / ``_geometry``, what the plan is built
+    from) against the reference's ``calibrate`` directly, not through the oracle: every state field equal."""
+    from multicamera_stitching_b200 import StitcherBase
+    h, w = 90, 160
+    imageA = synthetic.make_frame(h, w, 3, 1, 0, "noise")
+    imageB = synthetic.make_frame(h + 12, w - 20, 3, 0, 0, "noise")
+    homs = [synthetic.make_homography(k, h, w, w - 20) for k in range(4)]
+    homs += [synthetic.homography_from_points(h, w, w - 20)] + random_homographies(24, h, w, seed=23)
+    for H in homs:
+        sb = ref.StitcherBase(sid="pin", super_mode=super_mode)
+        inject_homography(sb, H)
+        sb.calibrate(images=(imageB, imageA), ratio=0.75, reprojThresh=3.0, xoffset=offsets[0], yoffset=offsets[1])
+        ours = StitcherBase(sid="pin", super_mode=super_mode)
+        ours.set_homography(np.array(H, dtype=np.float64), shapeA=imageA.shape, shapeB=imageB.shape,
+                            xoffset=offsets[0], yoffset=offsets[1])
+        assert_state_equal(sb, {f: getattr(ours, f) for f in FIELDS})
+
+
 # ---- a1: pair stitch (StitcherClass.py:211-256) ----------------------------------------------------
 @pytest.mark.parametrize("super_mode", [False, True])
 @pytest.mark.parametrize("kind", ["noise", "smooth"])
