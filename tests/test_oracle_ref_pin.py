@@ -341,3 +341,34 @@ def test_prebuilt_reference_runs_without_the_reference_tree(tmp_path):
     env = dict(os.environ, MCS_REFERENCE_ROOT=str(tmp_path / "no_reference_here"))
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
     assert r.returncode == 0 and b"prebuilt ok" in r.stdout, r.stdout.decode(errors="replace")
+
+
+def test_product_lifecycle_equals_reference(ref):
+    """a7 directly against the reference objects: labels, ``__str__``, ``params_to_list`` / ``params_to_array``
+    round trip and ``reset`` leave the product's stages in the state the reference's are in."""
+    from multicamera_stitching_b200 import Stitcher
+    h, w, n = 72, 110, 4
+    images = synthetic.make_frames(n, h, w, 3, frame_index=2, kind="noise")
+    labels = stitcher_ref.sorted_labels(images)
+    homs = [synthetic.make_homography(k, h, w, w) for k in range(n - 1)]
+    rs = reference_chain(ref, images, homs, False)
+    ours = Stitcher(images)
+    ours.calibrate_from_homographies([images[l].shape for l in labels], homs, xoffset=0, yoffset=0)   # :102-103
+    assert list(ours.img_labels) == list(rs.img_labels) and list(ours.stitcher_labels) == list(rs.stitcher_labels)
+    for a, b in zip(rs.stitchers, ours.stitchers):
+        assert a.sid == b.sid
+        assert str(a).split("| Matches:")[0] == str(b).split("| Matches:")[0]          # the injected calibration
+        assert str(a).split("StitcherSize:")[1] == str(b).split("StitcherSize:")[1]   # carries stand-in matches
+        a.params_to_list()
+        b.params_to_list()
+        for f in ("cachedAH", "cachedAINVH", "cachedBH", "cachedBINVH"):
+            assert type(getattr(a, f)) is type(getattr(b, f)) is list
+            assert np.array_equal(np.asarray(getattr(a, f)), np.asarray(getattr(b, f)))
+        a.params_to_array()
+        b.params_to_array()
+        assert_state_equal(a, {f: getattr(b, f) for f in FIELDS})
+        a.reset()
+        b.reset()
+        for f in FIELDS + ("matches", "status"):
+            assert getattr(a, f) is None and getattr(b, f) is None, f
+        assert str(a) == str(b)
