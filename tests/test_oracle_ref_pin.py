@@ -372,3 +372,26 @@ def test_product_lifecycle_equals_reference(ref):
         for f in FIELDS + ("matches", "status"):
             assert getattr(a, f) is None and getattr(b, f) is None, f
         assert str(a) == str(b)
+
+
+def test_product_fallbacks_equal_reference(ref):
+    """The frame path never raises (SURVEY section 8 b): an uncalibrated chain hands the first image through
+    (:255-256), a dictionary with fewer images than labels hands back the last label's image (:124-128) - the
+    product returns the very objects the reference returns, without touching a device."""
+    from multicamera_stitching_b200 import Stitcher
+    images = synthetic.make_frames(3, 48, 64, 3, frame_index=0, kind="noise")
+    rs, ours = ref.Stitcher(images, super_mode=False), Stitcher(images)
+    labels = list(rs.img_labels)
+    assert rs.stitch(images) is images[labels[0]] and ours.stitch(images) is images[labels[0]]
+    short = {l: images[l] for l in labels[1:]}                     # one image missing: the last label's image comes back
+    assert rs.stitch(short) is images[labels[-1]] and ours.stitch(short) is images[labels[-1]]
+    short = {l: images[l] for l in labels[:2]}                     # the last label itself missing: both look it up
+    with pytest.raises(KeyError):
+        rs.stitch(short)
+    with pytest.raises(KeyError):
+        ours.stitch(short)
+    short = {labels[-1]: images[labels[-1]]}
+    assert rs.stitch(short) is images[labels[-1]] and ours.stitch(short) is images[labels[-1]]
+    pair_r, pair_o = rs.stitchers[0], ours.stitchers[0]
+    b, a = images[labels[0]], images[labels[1]]
+    assert pair_r.stitch((b, a)) is b and pair_o.stitch((b, a)) is b
