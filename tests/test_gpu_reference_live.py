@@ -46,3 +46,32 @@ def test_cuda_pair_equals_the_reference_class(cuda_device, ref):
     rs = build_ref.calibrated_stitcher(ref, images, homographies)
     pair = (images[labels[0]], images[labels[1]])
     assert np.array_equal(st.stitchers[0].stitch(pair), rs.stitchers[0].stitch(images=pair))
+
+
+def test_cuda_match_keypoints_equals_the_reference_class(cuda_device, ref):
+    """``StitcherBase.matchKeypoints`` (StitcherClass.py:405-448) with float descriptors, the reference's own SIFT
+    branch: the match list of the GPU path (L2 2-NN + ratio test) equals the reference method's; the homography
+    agrees with the reference's ``findHomography`` result within 0.5 px on the matched points' extent (different
+    RANSAC sampling, same inliers' least-squares fit)."""
+    from multicamera_stitching_b200 import StitcherBase
+    rng = np.random.default_rng(5)
+    nA, nB = 700, 800
+    featB = np.rint(rng.normal(0, 40, (nB, 128)).clip(0, 255)).astype(np.float32)      # SIFT descriptors are
+    perm = rng.permutation(nB)[:nA]                                                    # integer-valued floats
+    featA = np.rint((featB[perm] + rng.normal(0, 6, (nA, 128))).clip(0, 255)).astype(np.float32)
+    featA[600:] = np.rint(rng.normal(0, 40, (100, 128)).clip(0, 255)).astype(np.float32)
+    H_true = np.array([[0.97, 0.02, 31.0], [-0.015, 1.01, 7.5], [1e-5, -2e-5, 1.0]])
+    kpsA = rng.uniform(0, 600, (nA, 2)).astype(np.float32)
+    proj = np.c_[kpsA, np.ones(nA)] @ H_true.T
+    kpsB = np.zeros((nB, 2), np.float32)
+    kpsB[perm] = (proj[:, :2] / proj[:, 2:]).astype(np.float32) + rng.normal(0, 0.3, (nA, 2)).astype(np.float32)
+    H0, m0, s0 = ref.StitcherBase().matchKeypoints(kpsA=kpsA, kpsB=kpsB, featuresA=featA, featuresB=featB,
+                                                   ratio=0.75, reprojThresh=3.0)
+    H1, m1, s1 = StitcherBase().matchKeypoints(kpsA=kpsA, kpsB=kpsB, featuresA=featA, featuresB=featB,
+                                               ratio=0.75, reprojThresh=3.0)
+    assert [tuple(m) for m in m1] == [tuple(m) for m in m0] and len(m0) > 400
+    corners = np.array([[0, 0, 1], [600, 0, 1], [600, 600, 1], [0, 600, 1]], dtype=np.float64)
+    p0, p1 = corners @ np.asarray(H0).T, corners @ np.asarray(H1).T
+    assert np.abs(p0[:, :2] / p0[:, 2:] - p1[:, :2] / p1[:, 2:]).max() < 0.5
+    assert np.asarray(s1).shape == np.asarray(s0).shape
+    assert (np.asarray(s1).ravel() != np.asarray(s0).ravel()).mean() < 0.02      # inlier masks agree on >= 98 %
