@@ -75,3 +75,18 @@ def test_cuda_match_keypoints_equals_the_reference_class(cuda_device, ref):
     assert np.abs(p0[:, :2] / p0[:, 2:] - p1[:, :2] / p1[:, 2:]).max() < 0.5
     assert np.asarray(s1).shape == np.asarray(s0).shape
     assert (np.asarray(s1).ravel() != np.asarray(s0).ravel()).mean() < 0.02      # inlier masks agree on >= 98 %
+
+
+@pytest.mark.parametrize("n,super_mode", [(3, False), (4, True)])
+def test_cuda_debug_overlays_equal_the_reference_class(cuda_device, ref, n, super_mode):
+    """``stitch(images_dic, draw_descriptors=True)``: the reference draws its overlay at every stage (:244-245), the
+    product composites once on the GPU and places each stage's overlay afterwards - the same picture."""
+    h, w = 120, 200
+    st, homographies, labels, images = synthetic.synthetic_stitcher(n, h, w, 3, super_mode=super_mode, kind="smooth")
+    rs = build_ref.calibrated_stitcher(ref, images, homographies, super_mode=super_mode)
+    for ours, theirs in zip(st.stitchers, rs.stitchers):
+        ours.sid = theirs.sid
+    want = rs.stitch(images, draw_descriptors=True)
+    got = st.stitch(images, draw_descriptors=True)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert not np.array_equal(got, st.stitch(images))      # something was drawn
