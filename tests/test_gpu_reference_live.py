@@ -90,3 +90,26 @@ def test_cuda_debug_overlays_equal_the_reference_class(cuda_device, ref, n, supe
     got = st.stitch(images, draw_descriptors=True)
     assert got.shape == want.shape and np.array_equal(got, want)
     assert not np.array_equal(got, st.stitch(images))      # something was drawn
+
+
+def test_cuda_shape_fixup_equals_the_reference_class(cuda_device, ref):
+    """Frames that do not have the calibrated size: the reference warns and resizes them with
+    ``cv2.resize(INTER_LINEAR)`` before it stitches (StitcherClass.py:226-233) - smaller and larger camera frames,
+    and a first image of the wrong size; the product resizes on the GPU and ends with the same panorama."""
+    import cv2
+    n, h, w = 4, 120, 200
+    st, homographies, labels, images = synthetic.synthetic_stitcher(n, h, w, 3, kind="noise")
+    rs = build_ref.calibrated_stitcher(ref, images, homographies)
+    cases = {
+        "one camera smaller": {2: (90, 150)},
+        "one camera larger": {1: (150, 260)},
+        "first image and last camera": {0: (96, 160), 3: (131, 217)},
+        "every frame halved": {k: (60, 100) for k in range(n)},
+    }
+    for name, sizes in cases.items():
+        frames = dict(images)
+        for k, (hh, ww) in sizes.items():
+            frames[labels[k]] = cv2.resize(images[labels[k]], (ww, hh), interpolation=cv2.INTER_AREA)
+        want = rs.stitch(frames)
+        got = st.stitch(frames)
+        assert got.shape == want.shape and np.array_equal(got, want), name
